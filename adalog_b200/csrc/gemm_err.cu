@@ -1,0 +1,433 @@
+// Candidate-batched GEMM with fused squared-error epilogue for sm_100a (tcgen05 + TMEM + TMA).
+//
+// One 128-row M tile = the 128 candidates of one "unit" (a token, a weight row, a Q/K/V row ...), so TMEM
+// lane p holds candidate p and every epilogue thread owns exactly one candidate: the per-candidate error is
+// accumulated in a register across the CTA's whole static work list with no cross-thread reduction, which
+// keeps equal candidates bit-equal (exact-tie parity, SURVEY.md section 7 hard part 1).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 4-7 = epilogue (TMEM lanes 32*(w%4)..).  Pipelines: smem full/empty ring (kStages) between TMA and
+// MMA; TMEM full/empty (2 accumulator stages of 256 columns) between MMA and epilogue.
+#include "common.cuh"
+#include "../../include/adalog_b200.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace adalog {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;                 // bf16 elements = one 128-byte swizzle row
+constexpr int kMaxBN = 256;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KiB
+constexpr uint32_t kBBytes = kMaxBN * kBK * 2;     // 32 KiB
+constexpr uint32_t kTmemCols = 512;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+struct __align__(16) SmemTail {
+  float ysm[2][kMaxBN];       // 16-byte aligned: read back as float4 broadcasts
+  float csm[2][kMaxBN];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tfull[kAccStages];
+  uint64_t tempty[kAccStages];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * (kABytes + kBBytes) + sizeof(SmemTail);
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s
+      printf("adalog gemm_err: mbarrier timeout (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 "version 1"):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored for swizzled K-major) | [32,46) SBO>>4 (8 rows*128B = 1024)
+//   [46,48) version=1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=F32 (bit4), A=BF16 (bit7), B=BF16 (bit10), K-major both, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct KArgs {
+  int KB, N, BN, NT, U, UG, upc, cpg;
+  long long brpg, g_base, u_base;
+  const float* y; long long ldy;
+  const float* rs; const float* rb; long long rs_div, rs_mod;
+  const float* cs; const float* cb;
+  double* partial;
+  float* dbg;   // debug mode: dump D[128, N] of the single tile
+};
+
+// ---------------------------------------------------------------- the kernel
+template <bool HAS_CS>
+__global__ void __launch_bounds__(kThreads, 1)
+cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)kStages * kABytes;
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)kStages * (kABytes + kBBytes));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // static work list of this CTA
+  const int g_local = blockIdx.x / a.cpg;
+  const int ci = blockIdx.x - g_local * a.cpg;
+  const int u0 = g_local * a.UG + ci * a.upc;
+  const int u1 = min(min(u0 + a.upc, (g_local + 1) * a.UG), a.U);
+  const int nt0 = (int)(((long long)blockIdx.y * a.NT) / gridDim.y);
+  const int nt1 = (int)(((long long)(blockIdx.y + 1) * a.NT) / gridDim.y);
+  const int n_units = max(u1 - u0, 0);
+  const int n_nt = nt1 - nt0;
+  const int n_tiles = n_units * n_nt;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tail->tfull[i], 1); mbar_init(&tail->tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                 "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx = kABytes + (uint32_t)a.BN * kBK * 2;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int u = u0 + t / n_nt;
+        const int nt = nt0 + t % n_nt;
+        const long long brow = (a.g_base + g_local) * a.brpg + (long long)nt * a.BN;
+        for (int kb = 0; kb < a.KB; ++kb) {
+          mbar_wait(&tail->empty[stage], phase ^ 1);
+          mbar_expect_tx(&tail->full[stage], tx);
+          tma_load_2d(&tmA, &tail->full[stage], sA + (size_t)stage * kABytes, kb * kBK, u * kBM);
+          tma_load_2d(&tmB, &tail->full[stage], sB + (size_t)stage * kBBytes, kb * kBK, (int)brow);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t idesc = make_idesc(a.BN);
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t as = t & 1, aphase = (t >> 1) & 1;
+        mbar_wait(&tail->tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kMaxBN;
+        for (int kb = 0; kb < a.KB; ++kb) {
+          mbar_wait(&tail->full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)stage * kABytes));
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&tail->empty[stage]);    // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tail->tfull[as]);         // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue: TMEM -> registers -> per-candidate squared error =====================
+    const int et = threadIdx.x - kEpiWarp0 * 32;            // 0..127 = candidate p = TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    double acc64 = 0.0;
+    float rs = 0.0f, rb = 0.0f;
+    long long cur_ri = -1;
+    float yreg[2] = {0.0f, 0.0f}, creg[2] = {0.0f, 0.0f};
+    auto prefetch = [&](int t) {
+      const int u = u0 + t / n_nt;
+      const int n0 = (nt0 + t % n_nt) * a.BN;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = n0 + et + j * 128;
+        float yv = 0.0f, cv = 0.0f;
+        if (et + j * 128 < a.BN && n < a.N) {
+          yv = __ldg(a.y + (long long)u * a.ldy + n);
+          if (HAS_CS) { yv -= __ldg(a.cb + n); cv = __ldg(a.cs + n); }
+        }
+        yreg[j] = yv; creg[j] = cv;
+      }
+    };
+    if (n_tiles > 0) prefetch(0);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int u = u0 + t / n_nt;
+      const int n0 = (nt0 + t % n_nt) * a.BN;
+      const int ncols = min(a.BN, a.N - n0);
+      const uint32_t as = t & 1, aphase = (t >> 1) & 1;
+      const int buf = t & 1;
+      tail->ysm[buf][et] = yreg[0];
+      if (et + 128 < kMaxBN) tail->ysm[buf][et + 128] = yreg[1];
+      if (HAS_CS) { tail->csm[buf][et] = creg[0]; tail->csm[buf][et + 128] = creg[1]; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t + 1 < n_tiles) prefetch(t + 1);
+      const long long ri = ((a.u_base + u) / a.rs_div) % a.rs_mod;
+      if (ri != cur_ri) {
+        cur_ri = ri;
+        rs = __ldg(a.rs + ri * kBM + et);
+        rb = a.rb ? __ldg(a.rb + ri * kBM + et) : 0.0f;
+      }
+      mbar_wait(&tail->tfull[as], aphase);
+      tc_fence_after();
+      float acc = 0.0f;
+      const uint32_t tbase = tmem_base + lane_base + as * kMaxBN;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t d[32];
+        tmem_ld32(tbase + c0, d);
+        tmem_ld_wait();
+        if (a.dbg) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = __uint_as_float(d[j]);
+        }
+        const int lim = min(32, ncols - c0);
+        if (lim == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 yv = *reinterpret_cast<const float4*>(&tail->ysm[buf][c0 + j]);
+            float4 cv = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (HAS_CS) cv = *reinterpret_cast<const float4*>(&tail->csm[buf][c0 + j]);
+            const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+            const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float dv = __uint_as_float(d[j + e]);
+              if (HAS_CS) dv *= c4[e];
+              const float diff = y4[e] - fmaf(rs, dv, rb);
+              acc = fmaf(diff, diff, acc);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < lim) {
+              float dv = __uint_as_float(d[j]);
+              if (HAS_CS) dv *= tail->csm[buf][c0 + j];
+              const float diff = tail->ysm[buf][c0 + j] - fmaf(rs, dv, rb);
+              acc = fmaf(diff, diff, acc);
+            }
+          }
+        }
+      }
+      acc64 += (double)acc;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->tempty[as]);
+    }
+    if (a.partial)
+      a.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * kBM + et] = acc64;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box [box_rows, 64], 128-byte swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  auto enc = get_encode();
+  if (!enc) return fail(-20, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(-21, "operand base not 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-22, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r,
+                                     (long long)rows, (long long)cols, box_rows);
+  return 0;
+}
+
+static int validate(const adalog_gemm_err_args* a) {
+  ADALOG_REQUIRE(a && a->A && a->Bm, -1, "cand_gemm_err: null operand");
+  ADALOG_REQUIRE(a->KB > 0 && a->N > 0 && a->U > 0 && a->UG > 0 && a->upc > 0 && a->S > 0, -1,
+                 "cand_gemm_err: non-positive size");
+  ADALOG_REQUIRE(a->BN >= 16 && a->BN <= kMaxBN && a->BN % 16 == 0, -1, "cand_gemm_err: BN must be a multiple of 16 in [16,256]");
+  ADALOG_REQUIRE(a->U % a->UG == 0, -1, "cand_gemm_err: U must be a multiple of UG");
+  ADALOG_REQUIRE(a->a_rows >= (int64_t)a->U * kBM, -1, "cand_gemm_err: A has fewer than U*128 rows");
+  ADALOG_REQUIRE(a->rs_div > 0 && a->rs_mod > 0 && a->rs, -1, "cand_gemm_err: row scale required");
+  ADALOG_REQUIRE((a->cs == nullptr) == (a->cb == nullptr), -1, "cand_gemm_err: cs and cb come together");
+  ADALOG_REQUIRE(a->y && a->partial, -1, "cand_gemm_err: y / partial required");
+  const int NT = (a->N + a->BN - 1) / a->BN;
+  ADALOG_REQUIRE(a->S <= NT, -1, "cand_gemm_err: more N splits than N tiles");
+  return 0;
+}
+
+static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st) {
+  KArgs k;
+  k.KB = a->KB; k.N = a->N; k.BN = a->BN; k.NT = (a->N + a->BN - 1) / a->BN; k.U = a->U; k.UG = a->UG; k.upc = a->upc;
+  k.cpg = (a->UG + a->upc - 1) / a->upc;
+  k.brpg = a->brpg; k.g_base = a->g_base; k.u_base = a->u_base;
+  k.y = a->y; k.ldy = a->ldy; k.rs = a->rs; k.rb = a->rb; k.rs_div = a->rs_div; k.rs_mod = a->rs_mod;
+  k.cs = a->cs; k.cb = a->cb; k.partial = a->partial; k.dbg = dbg;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, a->A, a->a_rows, (int64_t)a->KB * kBK, kBM);
+  if (rc) return rc;
+  rc = make_map(&tmB, a->Bm, a->b_rows, (int64_t)a->KB * kBK, a->BN);
+  if (rc) return rc;
+  dim3 grid((unsigned)((a->U / a->UG) * k.cpg), (unsigned)a->S);
+  if (a->cs) {
+    cudaFuncSetAttribute(cand_gemm_err_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cand_gemm_err_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);
+  } else {
+    cudaFuncSetAttribute(cand_gemm_err_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cand_gemm_err_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);
+  }
+  return check_launch("cand_gemm_err");
+}
+
+}  // namespace adalog
+
+using namespace adalog;
+
+extern "C" {
+
+int adalog_cand_gemm_err_grid(const adalog_gemm_err_args* a) {
+  int rc = validate(a);
+  if (rc) return rc;
+  return (a->U / a->UG) * ((a->UG + a->upc - 1) / a->upc);
+}
+
+int adalog_cand_gemm_err(const adalog_gemm_err_args* a, void* stream) {
+  int rc = validate(a);
+  if (rc) return rc;
+  return launch(a, nullptr, (cudaStream_t)stream);
+}
+
+int adalog_debug_gemm_tile(const uint16_t* A, const uint16_t* Bm, int KB, int N, float* D, void* stream) {
+  ADALOG_REQUIRE(A && Bm && D && KB > 0 && N > 0, -1, "debug_gemm_tile: bad arguments");
+  // y = 0, rs = 1: scratch taken from D's tail is not available, so use small static device buffers
+  static float* zeros = nullptr;
+  static float* ones = nullptr;
+  static double* part = nullptr;
+  if (!zeros) {
+    float h1[kBM];
+    for (int i = 0; i < kBM; ++i) h1[i] = 1.0f;
+    if (cudaMalloc(&zeros, 65536 * sizeof(float)) != cudaSuccess || cudaMalloc(&ones, kBM * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&part, 64 * kBM * sizeof(double)) != cudaSuccess)
+      return fail(-30, "debug_gemm_tile: cudaMalloc failed");
+    cudaMemset(zeros, 0, 65536 * sizeof(float));
+    cudaMemcpy(ones, h1, sizeof(h1), cudaMemcpyHostToDevice);
+  }
+  ADALOG_REQUIRE(N <= 65536, -1, "debug_gemm_tile: N too large");
+  adalog_gemm_err_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.Bm = Bm; a.a_rows = kBM; a.b_rows = N; a.KB = KB; a.N = N;
+  a.BN = N >= kMaxBN ? kMaxBN : ((N + 15) / 16) * 16;
+  a.U = 1; a.UG = 1; a.upc = 1; a.S = 1; a.brpg = N; a.g_base = 0; a.u_base = 0;
+  a.y = zeros; a.ldy = 0; a.rs = ones; a.rb = nullptr; a.rs_div = 1; a.rs_mod = 1; a.cs = nullptr; a.cb = nullptr;
+  a.partial = part;
+  int rc = validate(&a);
+  if (rc) return rc;
+  return launch(&a, D, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+"""Thin torch-tensor wrappers over the C ABI (include/adalog_b200.h).
+
+Every function takes CUDA float32 tensors, enqueues on torch's current stream and returns tensors.
+No CPU path exists: CPU tensors raise AdalogError.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import AdalogError, GemmErrArgs, call
+
+P_TILE = 128   # ADALOG_P
+BK = 64        # ADALOG_BK
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise AdalogError('adalog_b200 kernels need CUDA tensors (there is no CPU fallback)')
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def kpad(K):
+    return ((K + BK - 1) // BK) * BK
+
+
+def _prod(xs):
+    r = 1
+    for v in xs:
+        r *= int(v)
+    return r
+
+
+def group_layout(x_shape, s_shape):
+    """How a broadcast scale maps onto flat x: group(i) = (i // inner) % ngroups."""
+    s_shape = list(s_shape)
+    while len(s_shape) > len(x_shape) and s_shape[0] == 1:
+        s_shape = s_shape[1:]
+    if _prod(s_shape) == 1:
+        return 1, 1
+    if len(s_shape) > len(x_shape):
+        raise AdalogError(f'scale shape {s_shape} does not broadcast onto {list(x_shape)}')
+    s = [1] * (len(x_shape) - len(s_shape)) + s_shape
+    nz = [i for i, d in enumerate(s) if d != 1]
+    d0, d1 = nz[0], nz[-1]
+    for i in range(d0, d1 + 1):
+        if s[i] != x_shape[i]:
+            raise AdalogError(f'scale shape {s_shape} does not broadcast onto {list(x_shape)}')
+    return _prod(x_shape[d1 + 1:]), _prod(x_shape[d0:d1 + 1])
+
+
+# ------------------------------------------------------------------------------------------ forwards
+def uniform_fakequant(x, scale, zero_point, n_levels, sym=False, want_codes=False, want_y=True):
+    """quantizers/uniform.py:25-36 on device."""
+    _cuda(x, scale, zero_point)
+    xc = _f32(x)
+    inner, ngroups = group_layout(xc.shape, scale.shape)
+    sc = _f32(scale.detach()).reshape(-1)
+    zr = None
+    if not sym:
+        z = _f32(zero_point.detach()).reshape(-1)
+        zr = (z.round() - z) + z                       # round_ste, _ste.py:5-6
+        if zr.numel() != sc.numel():
+            zr = zr.expand_as(sc).contiguous()
+    y = torch.empty_like(xc) if want_y else None
+    codes = torch.empty(xc.shape, dtype=torch.int16, device=xc.device) if want_codes else None
+    call('adalog_uniform_fakequant_f32', _p(xc), _p(y), _p(codes), xc.numel(), _p(sc), _p(zr), inner, ngroups,
+         int(n_levels), int(bool(sym)), _stream())
+    if want_codes:
+        return (y, codes) if want_y else codes
+    return y
+
+
+LOG2, LOGSQRT2, ADALOG = 0, 1, 2
+
+
+def log_fakequant(x, scale, kind, n_levels, q=None, table1=None, table2=None, shift=None, sub_shift=False,
+                  want_codes=False):
+    """quantizers/logarithm.py forwards (inference branch) on device; per-tensor scale."""
+    _cuda(x, scale, q, table1, table2, shift)
+    xc = _f32(x)
+    if scale.numel() != 1:
+        raise AdalogError('log-family quantizers take a per-tensor scale')
+    sc = _f32(scale.detach()).reshape(-1)
+    y = torch.empty_like(xc)
+    codes = torch.empty(xc.shape, dtype=torch.int16, device=xc.device) if want_codes else None
+    qq = q.detach().to(torch.int64).contiguous() if q is not None else None
+    t1 = _f32(table1) if table1 is not None else None
+    t2 = _f32(table2) if table2 is not None else None
+    sh = _f32(shift.detach()).reshape(-1) if shift is not None else None
+    call('adalog_log_fakequant_f32', _p(xc), _p(y), _p(codes), xc.numel(), _p(sc), int(kind), int(n_levels), _p(qq),
+         _p(t1), _p(t2), _p(sh), int(bool(sub_shift)), _stream())
+    return (y, codes) if want_codes else y
+
+
+def twin_fakequant(x, scale2, n_levels):
+    _cuda(x, scale2)
+    xc = _f32(x)
+    y = torch.empty_like(xc)
+    call('adalog_twin_fakequant_f32', _p(xc), _p(y), xc.numel(), _p(_f32(scale2.detach()).reshape(-1)), int(n_levels),
+         _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------ self sweeps
+def sweep_err_w_self(W2d, cs, cz, n_levels):
+    """W2d [R,K]; cs/cz [P,R] -> FP64 [P,R] = sum_k (w - dequant_p(w))^2   (linear.py:296-309)."""
+    _cuda(W2d, cs, cz)
+    W2d, cs, cz = _f32(W2d), _f32(cs), _f32(cz)
+    R, K = W2d.shape
+    P = cs.shape[0]
+    out = torch.empty(P, R, dtype=torch.float64, device=W2d.device)
+    call('adalog_sweep_err_w_self', _p(W2d), R, K, _p(cs), _p(cz), P, int(n_levels), _p(out), _stream())
+    return out
+
+
+def sweep_err_a_self(x, cs, cz, n_levels, per_channel):
+    """x [..., C]; cs/cz [C|1, P] -> FP64 [C|1, P] = sum over all rows of (x - dequant_p(x))^2."""
+    _cuda(x, cs, cz)
+    xc, cs, cz = _f32(x), _f32(cs), _f32(cz)
+    C = xc.shape[-1]
+    G, P = cs.shape
+    n = xc.numel()
+    cw = C if per_channel else 32
+    rows = (n + cw - 1) // cw
+    col_tiles = (cw + 31) // 32
+    nsplit = int(max(1, min(rows, (148 * 8 + col_tiles - 1) // col_tiles)))
+    partial = torch.empty(nsplit, C if per_channel else 1, P, dtype=torch.float64, device=xc.device)
+    call('adalog_sweep_err_a_self', _p(xc), n, C, int(bool(per_channel)), _p(cs), _p(cz), P, int(n_levels),
+         _p(partial), nsplit, _stream())
+    return partial.sum(dim=0)
+
+
+# ------------------------------------------------------------------------------------------ generators
+def _rows2d(x):
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise AdalogError('generator inputs are 2-D with unit K stride')
+    return x
+
+
+def gen_uniform_fixed(x2d, scale_g, zp_g, g_div, g_mod, n_levels, want_rowsum=False):
+    _cuda(x2d, scale_g, zp_g)
+    x2d = _rows2d(_f32(x2d))
+    R, K = x2d.shape
+    kp = kpad(K)
+    out = torch.empty(R, kp, dtype=torch.bfloat16, device=x2d.device)
+    rowsum = torch.empty(R, dtype=torch.float32, device=x2d.device) if want_rowsum else None
+    call('adalog_gen_uniform_fixed', _p(x2d), R, K, x2d.stride(0), _p(_f32(scale_g).reshape(-1)),
+         _p(_f32(zp_g).reshape(-1)), int(g_div), int(g_mod), int(n_levels), _p(out), kp, _p(rowsum), _stream())
+    return out, rowsum
+
+
+def gen_uniform_cand(x2d, u0, nu, cs, cz, P, pstride, gstride, g_div, g_mod, n_levels, out, krep=1, rowsum=None):
+    """rows [u0, u0+nu) of x2d -> out[(u*128+p), krep*kpad]."""
+    K = x2d.shape[1]
+    xs = x2d[u0:u0 + nu]
+    call('adalog_gen_uniform_cand', _p(xs), nu, K, x2d.stride(0), _p(cs), _p(cz), int(P), int(pstride), int(gstride),
+         int(g_div), int(g_mod), int(u0), int(n_levels), _p(out), kpad(K), int(krep), _p(rowsum), _stream())
+
+
+def gen_log_cand(x2d, u0, nu, cs, cq, P, shift, mtab, n_levels, out):
+    K = x2d.shape[1]
+    xs = x2d[u0:u0 + nu]
+    call('adalog_gen_log_cand', _p(xs), nu, K, x2d.stride(0), _p(cs), _p(cq), int(P), _p(shift), _p(mtab),
+         int(n_levels), _p(out), kpad(K), _stream())
+
+
+def gen_log_fixed(x2d, scale, q, shift, table1, m2, n_levels):
+    _cuda(x2d, scale, q, table1, m2)
+    x2d = _rows2d(_f32(x2d))
+    R, K = x2d.shape
+    kp = kpad(K)
+    out = torch.empty(R, kp, dtype=torch.bfloat16, device=x2d.device)
+    call('adalog_gen_log_fixed', _p(x2d), R, K, x2d.stride(0), _p(_f32(scale.detach()).reshape(-1)),
+         _p(q.detach().to(torch.int64).contiguous()), _p(_f32(shift.detach()).reshape(-1)) if shift is not None else None,
+         _p(_f32(table1)), _p(_f32(m2)), int(n_levels), _p(out), kp, _stream())
+    return out
+
+
+def gen_split3(x2d):
+    _cuda(x2d)
+    x2d = _rows2d(_f32(x2d))
+    R, K = x2d.shape
+    kp = kpad(K)
+    out = torch.empty(R, 3 * kp, dtype=torch.bfloat16, device=x2d.device)
+    call('adalog_gen_split3', _p(x2d), R, K, x2d.stride(0), _p(out), kp, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ candidate GEMM
+def pick_bn(N):
+    nt = (N + 255) // 256
+    bn = ((math.ceil(N / nt) + 15) // 16) * 16
+    return min(256, max(16, bn))
+
+
+def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, ldy, rs, rb, rs_div, rs_mod, cs, cb,
+                  upc, S, BN=None):
+    """One launch of adalog_cand_gemm_err.  Returns FP64 partial [S, gridX, 128]."""
+    BN = BN or pick_bn(N)
+    a = GemmErrArgs()
+    a.A, a.Bm = A.data_ptr(), Bm.data_ptr()
+    a.a_rows, a.b_rows = int(a_rows), int(Bm.shape[0])
+    a.KB, a.N, a.BN, a.U, a.UG, a.upc, a.S = ka // BK, int(N), int(BN), int(U), int(UG), int(upc), int(S)
+    a.brpg, a.g_base, a.u_base = int(brpg), int(g_base), int(u_base)
+    a.y, a.ldy = y.data_ptr() + 4 * int(y_off), int(ldy)
+    a.rs, a.rb = rs.data_ptr(), (rb.data_ptr() if rb is not None else None)
+    a.rs_div, a.rs_mod = int(rs_div), int(rs_mod)
+    a.cs, a.cb = (cs.data_ptr() if cs is not None else None), (cb.data_ptr() if cb is not None else None)
+    gx = call('adalog_cand_gemm_err_grid', ctypes.byref(a))
+    partial = torch.empty(S, gx, P_TILE, dtype=torch.float64, device=Bm.device)
+    a.partial = partial.data_ptr()
+    call('adalog_cand_gemm_err', ctypes.byref(a), _stream())
+    return partial
+
+
+def debug_gemm_tile(A, Bm):
+    """D[128, N] = A[128, ka] @ Bm[N, ka]^T through the tcgen05 pipeline (test hook)."""
+    _cuda(A, Bm)
+    assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16 and A.shape[0] == 128
+    ka = A.shape[1]
+    N = Bm.shape[0]
+    D = torch.zeros(128, N, dtype=torch.float32, device=A.device)
+    call('adalog_debug_gemm_tile', _p(A.contiguous()), _p(Bm.contiguous()), ka // BK, N, _p(D), _stream())
+    return D
+
+
+def version():
+    return _lib.load().adalog_version()

@@ -1,0 +1,82 @@
+"""Fast Progressive Combining Search driver shared by every quant layer.
+
+One routine replaces the four near-identical loops of the reference (linear.py:483-523, :941-967,
+matmul.py:243-262, conv.py:292-311).  The candidate arithmetic (linspace, -0.5, * delta, / (cnt-0.5),
+gather, repeat_interleave) is kept op-for-op in FP32 so that candidate bits equal the reference's; the
+scoring itself is delegated to `score(scales, aux, topk) -> indices`, i.e. to the CUDA sweeps.
+"""
+import torch
+
+
+def candidate_chunks(P, tile=128):
+    """slices of at most `tile` candidates (the kernels score one TMEM-lane tile of 128 per pass)"""
+    return [(p0, min(P, p0 + tile)) for p0 in range(0, P, tile)]
+
+
+def refine(scales, aux, delta, score, axis, new_cnt, width, steps, floor=None):
+    """Refinement steps 1..steps of FPCS starting from an already built first grid.
+
+    scales/aux: candidate tensors with the candidate axis at `axis` (0 or -1); aux carries zero points
+    (or log bases, linear.py:961); delta: grid pitch along the scale axis.
+    """
+    dev = scales.device
+    idx = score(scales, aux, width)
+    best_s = torch.gather(scales, dim=axis, index=idx)
+    best_a = torch.gather(aux, dim=axis, index=idx)
+    left = steps - 1
+    while left > 0:
+        ramp = torch.linspace(0, 1, steps=new_cnt).to(dev)
+        if axis == 0:
+            offs = (ramp.view(-1, *([1] * (scales.dim() - 1))) - 0.5) * delta
+            delta = delta / (new_cnt - 0.5)
+            scales = (best_s.unsqueeze(1) + offs.unsqueeze(0)).reshape(-1, *scales.shape[1:])
+            aux = best_a.repeat_interleave(new_cnt, dim=0)
+        else:
+            offs = (ramp[None, :] - 0.5) * delta
+            delta = delta / (new_cnt - 0.5)
+            scales = (best_s.unsqueeze(-1) + offs.unsqueeze(-2)).reshape(*scales.shape[:-1], -1)
+            if floor is not None:
+                scales = scales.clamp(min=floor)
+            aux = best_a.repeat_interleave(new_cnt, dim=-1)
+        idx = score(scales, aux, 1 if left == 1 else width)
+        if left > 1:
+            best_s = torch.gather(scales, dim=axis, index=idx)
+            best_a = torch.gather(aux, dim=axis, index=idx)
+        left -= 1
+
+
+def search(scales, aux, score, axis, eq_n, width=16, steps=6, floor=None):
+    """Full FPCS: first grid -> top `width` -> (steps-1) refinements of eq_n/width points each."""
+    delta = (scales[1:2] - scales[0:1]) if axis == 0 else (scales[:, 1:2] - scales[:, 0:1])
+    refine(scales, aux, delta, score, axis, int(eq_n / width), width, steps, floor)
+
+
+def percentile_grid(delta_min, delta_max, n_levels, num_zp, num_scale, axis, lead_dims=0):
+    """scale x zero-point grid with index p = zp_idx * num_scale + scale_idx
+    (linear.py:442-451, :472-481; matmul.py:231-240; conv.py:281-290)."""
+    dev = delta_min.device
+    ramp = torch.linspace(0, 1, steps=num_scale).to(dev)
+    zp_lo = int(n_levels - num_zp / 2)
+    zp_hi = int(n_levels + num_zp / 2)
+    zps = torch.tensor(range(zp_lo, zp_hi)).to(dev).repeat_interleave(num_scale)
+    if axis == 0:
+        ones = [1] * lead_dims
+        scales = (delta_min + ramp.view(-1, *ones) * (delta_max - delta_min)).repeat(num_zp, *ones) / (2 * n_levels - 1)
+        zps = zps.view(-1, *ones).repeat(1, *scales.shape[1:])
+    else:
+        scales = (delta_min + ramp[None, :] * (delta_max - delta_min)).repeat(1, num_zp) / (2 * n_levels - 1)
+        zps = zps[None, :].repeat(scales.shape[0], 1)
+    return scales, zps
+
+
+def chunked_quantile(x2, pct):
+    """quantile over the last dim of x2 = x.view(g, 1, -1), doubling the middle dim until the reduced dim fits
+    torch.quantile's 2^24 limit, then averaging the chunk quantiles (linear.py:465-471, matmul.py:223-230)."""
+    g = x2.shape[0]
+    mbs = 1
+    while x2.numel() // (g * mbs) > (1 << 24):
+        mbs *= 2
+    x2 = x2.reshape(g, mbs, -1)
+    up = torch.quantile(x2, pct.to(x2.device), dim=-1).mean(dim=-1)
+    lo = torch.quantile(x2, (1 - pct).to(x2.device), dim=-1).mean(dim=-1)
+    return up, lo        # each [2, g]

@@ -1,0 +1,399 @@
+"""Per-evaluation candidate sweeps: the device replacements of the reference's `_search_best_*` bodies.
+
+Each function scores P <= 128 candidates on all calibration samples held by this rank and returns the
+reference's *similarity* tensor (= -error, FP32, same shape as the tensor the reference hands to
+torch.topk), accumulated in FP64 on a static partition so equal candidates get bit-equal scores.
+Under torch.distributed the FP64 sums are all-reduced before normalisation (utils/dist.py).
+
+Factorisation used by every GEMM sweep: fake-quantised operands are
+(integer) x scale, so the tensor cores multiply the exact integer parts in bf16 with FP32 accumulation
+and the scales, biases and shift corrections are applied in the fused epilogue.
+"""
+import math
+import os
+
+import torch
+
+from . import ops
+from .utils import dist as adist
+
+WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '96')) << 20
+NUM_SMS = 148
+R_BASE = 37.0
+
+_workspaces = {}
+
+
+def _workspace(device, n_elems):
+    key = (device.type, device.index)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < n_elems:
+        buf = torch.empty(n_elems, dtype=torch.bfloat16, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def release_workspaces():
+    _workspaces.clear()
+
+
+def require_cuda(device):
+    """The sweeps exist only as sm_100a kernels: refuse to run anywhere else (no CPU fallback)."""
+    if device.type != 'cuda':
+        raise EnvironmentError('CUDA is not available for this module: adalog_b200 has no CPU path')
+
+
+def _pad128(t, dim=-1):
+    """repeat the last candidate up to 128 entries along `dim` (pad rows are ignored by the caller)."""
+    P = t.shape[dim]
+    if P == ops.P_TILE:
+        return t
+    idx = torch.clamp(torch.arange(ops.P_TILE, device=t.device), max=P - 1)
+    return t.index_select(dim, idx)
+
+
+def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=1, rs_mod=1, cs=None, cb=None):
+    """Chunk the units through the bf16 workspace: generate candidate rows, launch the fused GEMM.
+
+    gen_cand(u0, nu, out) fills out[nu*128, ka] for units [u0, u0+nu).
+    UG == U: one group (linear): returns [n_launch, 128]; else whole groups per launch: returns [U/UG, 128].
+    """
+    dev = Bm.device
+    single = UG == U
+    max_units = max(1, WS_BYTES // (ops.P_TILE * ka * 2))
+    step = min(U, max_units) if single else min(U, max(1, max_units // UG) * UG)
+    ws = _workspace(dev, step * ops.P_TILE * ka)
+    BN = ops.pick_bn(N)
+    NT = (N + BN - 1) // BN
+    outs = []
+    for u0 in range(0, U, step):
+        nu = min(step, U - u0)
+        gen_cand(u0, nu, ws)
+        ug = nu if single else UG
+        groups = nu // ug
+        want = max(NUM_SMS, min(NUM_SMS * 4, (nu * NT) // 8))
+        upc = min(ug, max(1, math.ceil(nu / want)))
+        cpg = math.ceil(ug / upc)
+        S = min(NT, max(1, round(want / (groups * cpg))))
+        part = ops.cand_gemm_err(ws, nu * ops.P_TILE, Bm, ka, N, nu, ug, brpg, 0 if single else u0 // UG, u0, y,
+                                 u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN)
+        outs.append(part.view(S, groups, cpg, ops.P_TILE).sum(dim=(0, 2)))
+    return torch.cat(outs, dim=0)
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _cand2d(cs, cz):
+    """reference candidate tensors (candidate axis first) -> contiguous [P, G] float32 pair."""
+    P = cs.shape[0]
+    return _f32(cs).reshape(P, -1), _f32(cz).reshape(P, -1)
+
+
+# ================================================================================================
+# Linear family
+# ================================================================================================
+class LinearCtx:
+    """Device-resident calibration tensors of one linear layer (raw_input / raw_out of the reference)."""
+
+    def __init__(self, raw_input, raw_out, out_features):
+        self.raw_input, self.raw_out = raw_input, raw_out
+        self.x2d = _f32(raw_input).reshape(-1, raw_input.shape[-1])
+        self.y2d = _f32(raw_out).reshape(-1, out_features)
+        self.n_samples = raw_input.shape[0]
+        self.tok_per_sample = self.x2d.shape[0] // self.n_samples
+        self._yT = None
+
+    @property
+    def yT(self):
+        if self._yT is None:
+            self._yT = self.y2d.t().contiguous()
+        return self._yT
+
+
+def uniform_operand_params(q):
+    """(scale, round_ste(zp)) flattened, from a UniformQuantizer-like object."""
+    s = _f32(q.scale).reshape(-1)
+    z = _f32(q.zero_point).reshape(-1)
+    return s, (z.round() - z) + z
+
+
+def search_table_ints(n_levels, device):
+    """integer numerators of the 37 live entries of the search LUT (linear.py:750-752 / matmul.py:313-315)."""
+    table = torch.tensor([2 ** (-j / R_BASE) for j in range(120)])
+    table_scale = 1. / (4 * n_levels - 2)
+    return torch.round(table / table_scale)[:37].contiguous().to(device)
+
+
+def linear_err_w_self(weight3, cs, cz, n_levels):
+    """linear.py:296-309 -> similarities [P, n_V, rows]."""
+    n_V, rows, in_f = weight3.shape
+    c2, z2 = _cand2d(cs, cz)
+    esum = ops.sweep_err_w_self(_f32(weight3).reshape(-1, in_f), c2, z2, n_levels)
+    return (-(esum / in_f)).float().reshape(cs.shape[0], n_V, rows)
+
+
+def linear_err_a_self(ctx, cs, cz, n_levels, channel_wise):
+    """linear.py:320-345 -> similarities [C|1, P]."""
+    esum = ops.sweep_err_a_self(ctx.x2d, _f32(cs), _f32(cz), n_levels, channel_wise)
+    esum = adist.all_reduce_sum(esum)
+    denom = ctx.tok_per_sample * (1 if channel_wise else ctx.x2d.shape[1])
+    return (-(esum / denom)).float()
+
+
+def _fixed_act_operand(ctx, aq):
+    """quant_input(x) as an exact bf16 operand + the epilogue factors it implies.
+
+    returns (Bm [tokens, ka], a_scale (python float tensor [1] FP64), shift or None)
+    uniform:       x_hat = a_scale * I
+    shift-adalog:  x_hat = a_scale/(4n-2) * (m 2^-e) - shift        (logarithm.py:127-135, not bias-reparamed)
+    """
+    if getattr(aq, 'is_log', False):
+        nl = aq.n_levels
+        m2 = torch.round(_f32(aq.table2) * (4 * nl - 2))
+        Bm = ops.gen_log_fixed(ctx.x2d, aq.scale, aq.q, aq.shift, aq.table1, m2, nl)
+        return Bm, _f32(aq.scale).double().reshape(1) / (4 * nl - 2), _f32(aq.shift).double().reshape(1)
+    s, z = uniform_operand_params(aq)
+    Bm, _ = ops.gen_uniform_fixed(ctx.x2d, s, z, 1 << 62, 1, aq.n_levels)
+    return Bm, s.double(), None
+
+
+def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
+    """linear.py:355-384 -> similarities [P, n_V, rows]."""
+    n_V, rows, in_f = weight3.shape
+    out_f = n_V * rows
+    P = cs.shape[0]
+    dev = weight3.device
+    c2, z2 = _cand2d(cs, cz)                         # [P, out]
+    Bm, a_scale, shift = _fixed_act_operand(ctx, aq)
+    ka = ops.kpad(in_f)
+    W2d = _f32(weight3).reshape(out_f, in_f)
+    c2p = _pad128(c2.t().contiguous())               # [out, 128] candidate scales per row
+    rs = (c2p.double() * a_scale).float().contiguous()
+    b = _f32(bias) if bias is not None else torch.zeros(out_f, device=dev)
+    rb = b.reshape(-1, 1).expand(out_f, ops.P_TILE).contiguous()
+    rowsum = torch.empty(out_f, ops.P_TILE, dtype=torch.float32, device=dev) if shift is not None else None
+
+    def gen(u0, nu, out):
+        ops.gen_uniform_cand(W2d, u0, nu, c2, z2, P, out_f, 1, 1, out_f, n_levels_w, out, 1,
+                             rowsum[u0:] if rowsum is not None else None)
+        if shift is not None:
+            # sum_k (v s - shift) w = s sum_k v w - shift sum_k w  (linear.py:879): fold the second term into the
+            # row bias, using the integer row sums the generator just produced (same stream, ordered)
+            rb[u0:u0 + nu] = (b[u0:u0 + nu].double().reshape(-1, 1)
+                              - shift * c2p[u0:u0 + nu].double() * rowsum[u0:u0 + nu].double()).float()
+
+    ntok = ctx.x2d.shape[0]
+    res = run_cand_gemm(gen, out_f, ka, 1, Bm, 0, ntok, ctx.yT, ntok, rs, rb, 1, out_f)
+    res = adist.all_reduce_sum(res)                  # [out, 128]
+    sims = -(res[:, :P] / ctx.tok_per_sample)
+    return sims.t().float().reshape(P, n_V, rows)
+
+
+def _fixed_weight_operand(weight3, wq):
+    n_V, rows, in_f = weight3.shape
+    s, z = uniform_operand_params(wq)
+    Bm, colsum = ops.gen_uniform_fixed(_f32(weight3).reshape(-1, in_f), s, z, 1, n_V * rows, wq.n_levels, True)
+    return Bm, s, colsum
+
+
+def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
+    """linear.py:394-423 -> similarities [1, P]."""
+    n_V, rows, in_f = weight3.shape
+    out_f = n_V * rows
+    P = cs.shape[-1]
+    dev = weight3.device
+    Bm, s_w, _ = _fixed_weight_operand(weight3, wq)
+    c1, z1 = _f32(cs).reshape(-1), _f32(cz).reshape(-1)
+    ka = ops.kpad(in_f)
+
+    def gen(u0, nu, out):
+        ops.gen_uniform_cand(ctx.x2d, u0, nu, c1, z1, P, 1, 0, 1 << 62, 1, n_levels_a, out)
+
+    rs = _pad128(c1).contiguous()
+    cb = _f32(bias) if bias is not None else torch.zeros(out_f, device=dev)
+    ntok = ctx.x2d.shape[0]
+    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb)
+    res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
+    return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
+
+
+def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
+    """linear.py:856-890 (cs None: base-only search at the quantizer's current scale) and :898-931 -> [1, P]."""
+    n_V, rows, in_f = weight3.shape
+    out_f = n_V * rows
+    P = cq.shape[-1]
+    dev = weight3.device
+    nl = aq.n_levels
+    Bm, s_w, colsum = _fixed_weight_operand(weight3, wq)
+    q1 = cq.detach().reshape(-1).to(torch.int64).contiguous()
+    if cs is None:
+        c1 = _f32(aq.scale).reshape(1).expand(P).contiguous()
+    else:
+        c1 = _f32(cs).reshape(-1)
+    shift = _f32(aq.shift).reshape(1)
+    mtab = search_table_ints(nl, dev)
+    ka = ops.kpad(in_f)
+
+    def gen(u0, nu, out):
+        ops.gen_log_cand(ctx.x2d, u0, nu, c1, q1, P, shift, mtab, nl, out)
+
+    rs = (_pad128(c1).double() / (4 * nl - 2)).float().contiguous()
+    b = _f32(bias).double() if bias is not None else torch.zeros(out_f, device=dev, dtype=torch.float64)
+    cb = (b - shift.double() * s_w.double() * colsum.double()).float().contiguous()
+    ntok = ctx.x2d.shape[0]
+    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb)
+    res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
+    return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
+
+
+# ================================================================================================
+# MatMul family.  A [B,H,S,Kd] @ Bop [B,H,Kd,S2]  (matmul.py:48-56)
+# ================================================================================================
+class MatMulCtx:
+    def __init__(self, A, B, raw_out):
+        self.raw_input, self.raw_out = [A, B], raw_out
+        A, B, raw_out = _f32(A), _f32(B), _f32(raw_out)
+        self.Bn, self.H, self.S1, self.Kd = A.shape
+        self.S2 = B.shape[-1]
+        self.A2d = A.reshape(-1, self.Kd)                                   # rows (b,h,s1)
+        self.Bt2d = B.transpose(-2, -1).contiguous().reshape(-1, self.Kd)   # rows (b,h,s2)
+        self.y2d = raw_out.reshape(-1, self.S2)                             # rows (b,h,s1), cols s2
+        self._yT = None
+        self._raw_out = raw_out
+
+    @property
+    def yT2d(self):
+        if self._yT is None:
+            self._yT = self._raw_out.transpose(-2, -1).contiguous().reshape(-1, self.S1)  # rows (b,h,s2), cols s1
+        return self._yT
+
+
+def _head_params(q, H):
+    s, z = uniform_operand_params(q)
+    if s.numel() == 1:
+        s, z = s.expand(H).contiguous(), z.expand(H).contiguous()
+    return s, z
+
+
+def _matmul_reduce(res, ctx, P, head_channel_wise, pool_heads, n_cols_total):
+    """res [B*H, 128] FP64 sums -> similarities in the reference's layout."""
+    res = res.view(ctx.Bn, ctx.H, ops.P_TILE).sum(dim=0)          # [H, 128]
+    res = adist.all_reduce_sum(res)
+    if head_channel_wise and not pool_heads:
+        return (-(res[:, :P] / n_cols_total)).t().float().contiguous()      # [P, H]
+    tot = res.sum(dim=0)
+    return (-(tot[:P] / (n_cols_total * ctx.H))).float()                    # [P]
+
+
+def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, head_channel_wise):
+    """matmul.py:135-163: candidates on A, fixed quantised B -> [P, H] (or [P])."""
+    P = cs.shape[0]
+    H = ctx.H
+    c2, z2 = _cand2d(cs, cz)                                     # [P, H] or [P, 1]
+    gs = 1 if c2.shape[1] == H else 0
+    sB, zB = _head_params(Bq, H)
+    Bm, _ = ops.gen_uniform_fixed(ctx.Bt2d, sB, zB, ctx.S2, H, Bq.n_levels)
+    ka = ops.kpad(ctx.Kd)
+
+    def gen(u0, nu, out):
+        ops.gen_uniform_cand(ctx.A2d, u0, nu, c2, z2, P, c2.shape[1], gs, ctx.S1, H, n_levels_A, out)
+
+    cfull = c2 if gs else c2.expand(P, H)
+    rs = (_pad128(cfull.t().contiguous()).double() * sB.double().reshape(H, 1)).float().contiguous()   # [H,128]
+    U = ctx.Bn * H * ctx.S1
+    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H)
+    return _matmul_reduce(res, ctx, P, head_channel_wise, False, ctx.S1 * ctx.S2)
+
+
+def _fixed_A_operand(ctx, Aq):
+    """quant_input_A(A) as a bf16 operand, rows (b,h,s1); returns (Bm, per-head scale FP64 [H])."""
+    H = ctx.H
+    if getattr(Aq, 'is_log', False):
+        nl = Aq.n_levels
+        m2 = torch.round(_f32(Aq.table2) * (4 * nl - 2))
+        Bm = ops.gen_log_fixed(ctx.A2d, Aq.scale, Aq.q, None, Aq.table1, m2, nl)
+        return Bm, (_f32(Aq.scale).double().reshape(1) / (4 * nl - 2)).expand(H)
+    sA, zA = _head_params(Aq, H)
+    Bm, _ = ops.gen_uniform_fixed(ctx.A2d, sA, zA, ctx.S1, H, Aq.n_levels)
+    return Bm, sA.double()
+
+
+def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, head_channel_wise):
+    """matmul.py:173-201: candidates on B (its rows are the columns of the product), fixed quantised A."""
+    P = cs.shape[0]
+    H = ctx.H
+    c2, z2 = _cand2d(cs, cz)
+    gs = 1 if c2.shape[1] == H else 0
+    Bm, sA = _fixed_A_operand(ctx, Aq)
+    ka = ops.kpad(ctx.Kd)
+
+    def gen(u0, nu, out):
+        ops.gen_uniform_cand(ctx.Bt2d, u0, nu, c2, z2, P, c2.shape[1], gs, ctx.S2, H, n_levels_B, out)
+
+    cfull = c2 if gs else c2.expand(P, H)
+    rs = (_pad128(cfull.t().contiguous()).double() * sA.reshape(H, 1)).float().contiguous()
+    U = ctx.Bn * H * ctx.S2
+    res = run_cand_gemm(gen, U, ka, ctx.S2, Bm, ctx.S1, ctx.S1, ctx.yT2d, ctx.S1, rs, None, ctx.S2, H)
+    return _matmul_reduce(res, ctx, P, head_channel_wise, False, ctx.S1 * ctx.S2)
+
+
+def matmul_err_A_log_base(ctx, Bq, cq, n_levels_A):
+    """matmul.py:321-351: candidate log bases on the post-softmax operand, all heads pooled -> [P, 1]."""
+    P = cq.shape[0]
+    H = ctx.H
+    dev = ctx.A2d.device
+    q1 = cq.detach().reshape(-1).to(torch.int64).contiguous()
+    sB, zB = _head_params(Bq, H)
+    Bm, _ = ops.gen_uniform_fixed(ctx.Bt2d, sB, zB, ctx.S2, H, Bq.n_levels)
+    mtab = search_table_ints(n_levels_A, dev)
+    ka = ops.kpad(ctx.Kd)
+
+    def gen(u0, nu, out):
+        ops.gen_log_cand(ctx.A2d, u0, nu, None, q1, P, None, mtab, n_levels_A, out)
+
+    rs = (sB.double().reshape(H, 1) / (4 * n_levels_A - 2)).expand(H, ops.P_TILE).float().contiguous()
+    U = ctx.Bn * H * ctx.S1
+    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H)
+    return _matmul_reduce(res, ctx, P, True, True, ctx.S1 * ctx.S2).reshape(P, 1)
+
+
+# ================================================================================================
+# Conv (patch embedding: kernel == stride, no padding) -- conv.py:226-256 with raw FP32 input (a_bit >= 8)
+# ================================================================================================
+class ConvCtx:
+    def __init__(self, raw_input, raw_out, kernel_size):
+        self.raw_input, self.raw_out = raw_input, raw_out
+        x, y = _f32(raw_input), _f32(raw_out)
+        Bn, ic, Hh, Ww = x.shape
+        kh, kw = kernel_size
+        oh, ow = Hh // kh, Ww // kw
+        patches = x.reshape(Bn, ic, oh, kh, ow, kw).permute(0, 2, 4, 1, 3, 5).reshape(Bn * oh * ow, ic * kh * kw)
+        self.n_samples = Bn
+        self.pos_per_sample = oh * ow
+        self.x3 = ops.gen_split3(patches.contiguous())                 # [tokens, 3*ka]
+        oc = y.shape[1]
+        self.yT = y.permute(1, 0, 2, 3).reshape(oc, -1).contiguous()   # [oc, tokens]
+        self.K = ic * kh * kw
+
+
+def conv_err_w(ctx, weight2d, bias, cs, cz, n_levels_w):
+    """conv.py:226-256 -> similarities [P, oc]."""
+    oc, K = weight2d.shape
+    P = cs.shape[0]
+    dev = weight2d.device
+    c2, z2 = _cand2d(cs, cz)                                       # [P, oc]
+    W2d = _f32(weight2d)
+    ka = 3 * ops.kpad(K)
+
+    def gen(u0, nu, out):
+        ops.gen_uniform_cand(W2d, u0, nu, c2, z2, P, oc, 1, 1, oc, n_levels_w, out, 3)
+
+    rs = _pad128(c2.t().contiguous()).contiguous()
+    b = _f32(bias) if bias is not None else torch.zeros(oc, device=dev)
+    rb = b.reshape(-1, 1).expand(oc, ops.P_TILE).contiguous()
+    ntok = ctx.yT.shape[1]
+    res = run_cand_gemm(gen, oc, ka, 1, ctx.x3, 0, ntok, ctx.yT, ntok, rs, rb, 1, oc)
+    res = adist.all_reduce_sum(res)
+    return (-(res[:, :P] / ctx.pos_per_sample)).t().float().contiguous()

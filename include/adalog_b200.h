@@ -1,0 +1,146 @@
+/*
+ * adalog_b200 -- C ABI of the B200 (sm_100a) kernels behind AdaLog's FPCS calibration sweep and
+ * fake-quant forward.
+ *
+ * The reference (GoatWu/AdaLog) has no FFI: its hot path is eager PyTorch inside
+ * quantizers/*.py and quant_layers/*.py.  Each entry point below replaces one eager-op chain of the
+ * reference; the citation after "replaces:" is the reference file:line whose arithmetic it computes.
+ * The host side that binds these (ctypes) is adalog_b200/_lib.py; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless named h_*; no allocation, no ownership transfer, no
+ *    global mutable state; workspaces are passed in by the caller.
+ *  - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); all work is enqueued
+ *    on it and the call returns without synchronising.
+ *  - return 0 on success, negative on error; adalog_last_error() returns a thread-local message.
+ *  - P (candidates per sweep) is at most 128 = one TMEM lane per candidate; callers pad.
+ *  - zero points are passed as float (the reference promotes int64 zp to float32 in
+ *    `(x/s).round_() + zp`, linear.py:304) and, for the quantizer forward, already passed through
+ *    round_ste (quantizers/_ste.py:5-6).
+ */
+#ifndef ADALOG_B200_H_
+#define ADALOG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADALOG_P 128          /* candidate rows of one unit tile */
+#define ADALOG_BK 64          /* bf16 elements per 128-byte swizzled K block */
+
+int adalog_version(void);
+const char* adalog_last_error(void);
+
+/* ---------------------------------------------------------------- quantizer forwards (K1/K2) */
+
+/* replaces: quantizers/uniform.py:25-36 (UniformQuantizer.forward, inference branch).
+ * group(i) = (i / inner) % ngroups selects scale[g], zp[g].  y and codes are optional (NULL).
+ * asym: c = clamp(rint(x/s) + zp, 0, 2n-1), y = (c - zp) * s ; sym: c = clamp(rint(x/s), -n, n-1), y = c*s */
+int adalog_uniform_fakequant_f32(const float* x, float* y, int16_t* codes, int64_t n, const float* scale,
+                                 const float* zp, int64_t inner, int64_t ngroups, int n_levels, int symmetric,
+                                 void* stream);
+
+/* replaces: quantizers/logarithm.py:25-35 (kind 0, Log2), :45-62 (kind 1, LogSqrt2), :83-99 (kind 2, AdaLog
+ * with table1/table2 LUTs and base q) and the Shift* wrappers :105-135.
+ * v = clamp((x + shift)/s, 1e-15, 1); c = rint(-log2(v) [*2 | *37/q]); y = dequant(c) * s * (c < 2n) [- shift].
+ * scale: [1]; q: int64 [1] (kind 2); shift: [1] or NULL; sub_shift: subtract the shift from the result. */
+int adalog_log_fakequant_f32(const float* x, float* y, int16_t* codes, int64_t n, const float* scale, int kind,
+                             int n_levels, const long long* q, const float* table1, const float* table2,
+                             const float* shift, int sub_shift, void* stream);
+
+/* replaces: quantizers/uniform.py:57-68 (TwinUniformQuantizer.forward); scale2 = {positive, negative}. */
+int adalog_twin_fakequant_f32(const float* x, float* y, int64_t n, const float* scale2, int n_levels, void* stream);
+
+/* ---------------------------------------------------------------- self-error sweeps (K3/K4) */
+
+/* replaces: quant_layers/linear.py:296-309 (_search_best_w_scale_self, error part).
+ * W [R,K]; candidates cs/cz laid out [P,R]; err_sum[p*R + r] = sum_k (w - dequant_p(w))^2 in FP64. */
+int adalog_sweep_err_w_self(const float* W, int R, int K, const float* cs, const float* cz, int P, int n_levels,
+                            double* err_sum, void* stream);
+
+/* replaces: quant_layers/linear.py:320-345 (_search_best_a_scale_self, error part).
+ * x is n_total floats viewed as rows of C columns.  per_channel: candidates [C,P] (column c uses row c);
+ * else candidates [1,P] shared.  partial is [nsplit, Cw, P] FP64 sums of (x - dequant_p(x))^2 with
+ * Cw = C (per_channel) or 32 (per tensor: the flat array is swept 32 lanes wide); caller sums splits. */
+int adalog_sweep_err_a_self(const float* x, int64_t n_total, int C, int per_channel, const float* cs,
+                            const float* cz, int P, int n_levels, double* partial, int nsplit, void* stream);
+
+/* ---------------------------------------------------------------- operand generators for the candidate GEMM
+ * All generators read FP32 rows with unit K stride and write bf16 rows of pitch `kpad` (multiple of 64,
+ * zero filled beyond K).  Values are the INTEGER part of the fake-quantised tensor (code - zp, or m*2^-e for
+ * the log family) which bf16 holds exactly; scales are applied in the GEMM epilogue. */
+
+/* fixed operand, uniform quantizer (the non-searched side: linear.py:373 quant_input / :406 quant_weight_bias,
+ * matmul.py:141,179).  group(r) = (r / g_div) % g_mod.  rowsum (optional) = sum_k value. */
+int adalog_gen_uniform_fixed(const float* x, int64_t R, int K, int64_t ldx, const float* scale, const float* zp,
+                             int64_t g_div, int64_t g_mod, int n_levels, uint16_t* out, int kpad, float* rowsum,
+                             void* stream);
+
+/* candidate operand, uniform quantizer (linear.py:369-370, :409-410, matmul.py:150-151, :188-189, conv.py:237-238).
+ * out row (u*128 + p); candidate p of unit u uses cs/cz[p*pstride + ((u_base+u)/g_div % g_mod)*gstride].
+ * krep in {1,3}: the K block is repeated krep times along the row (pitch krep*kpad) to pair with a split-3 operand. */
+int adalog_gen_uniform_cand(const float* x, int64_t U, int K, int64_t ldx, const float* cs, const float* cz, int P,
+                            int64_t pstride, int64_t gstride, int64_t g_div, int64_t g_mod, int64_t u_base,
+                            int n_levels, uint16_t* out, int kpad, int krep, float* rowsum, void* stream);
+
+/* candidate operand, AdaLog search form (linear.py:872-878, :913-919; matmul.py:337-342).
+ * per candidate p: scale cs[p] (NULL: unscaled & unclamped, the post-softmax form) and base cq[p] (int64);
+ * value = mtab[(c*q) % 37] * 2^-floor(c*q/37), 0 where c >= 2n.  mtab: 37 floats holding integers. */
+int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const float* cs, const long long* cq, int P,
+                        const float* shift, const float* mtab, int n_levels, uint16_t* out, int kpad, void* stream);
+
+/* fixed operand, AdaLog inference form (logarithm.py:87-99 via matmul.py:179 / linear.py:373):
+ * value = m2[c] * 2^-table1[c] with m2 = table2*(4n-2) (integers), 0 where masked. */
+int adalog_gen_log_fixed(const float* x, int64_t R, int K, int64_t ldx, const float* scale, const long long* q,
+                         const float* shift, const float* table1, const float* m2, int n_levels, uint16_t* out,
+                         int kpad, void* stream);
+
+/* fixed operand, unquantised FP32 (conv.py:55-58 with a_bit >= 8): x = h + m + l, three bf16 pieces laid out
+ * [R, 3*kpad] so that a krep=3 candidate operand reproduces the FP32 product to 2^-24. */
+int adalog_gen_split3(const float* x, int64_t R, int K, int64_t ldx, uint16_t* out, int kpad, void* stream);
+
+/* ---------------------------------------------------------------- candidate-batched GEMM + fused error (K5-K10)
+ * replaces: the F.linear / @ / F.conv2d + _get_similarity + mean/sum chains of linear.py:355-384, :394-423,
+ * :856-890, :898-931, matmul.py:135-163, :173-201, :321-351, conv.py:226-256.
+ *
+ * A  [U*128, ka] bf16  : candidate operand, one 128-row tile per unit (row = u*128 + p), ka = KB*64.
+ * Bm [G*brpg, ka] bf16 : fixed operand, group g = (g_base + u/UG) owns rows [g*brpg, g*brpg + N).
+ * D[p, n] = sum_k A[u*128+p, k] * Bm[g*brpg + n, k]        (tcgen05.mma, FP32 accumulate in TMEM)
+ * yhat    = rs[ri+p] * (cs ? cs[n]*D : D) + (rb ? rb[ri+p] : 0),  ri = ((u_base+u)/rs_div % rs_mod)*128
+ * e[p]   += (y[u*ldy + n] - (cb ? cb[n] : 0) - yhat)^2      summed over the CTA's units and N tiles
+ * partial[(blockIdx.y*gridDim.x + blockIdx.x)*128 + p] = e[p] (FP64).  gridDim = (G_chunk * cpg, S):
+ * CTA x handles units [g*UG + ci*upc, +upc) of group g = x / cpg, ci = x % cpg; CTA y handles N tiles
+ * [y*NT/S, (y+1)*NT/S).  The partition is static, so equal candidates produce bit-equal sums. */
+typedef struct {
+  const uint16_t* A;  const uint16_t* Bm;
+  int64_t a_rows;     int64_t b_rows;      /* allocated rows of A / Bm (TMA bounds) */
+  int32_t KB;         /* K blocks of 64 */
+  int32_t N;          /* valid columns per group */
+  int32_t BN;         /* tile width, multiple of 16, <= 256 */
+  int32_t U;          /* units in this launch */
+  int32_t UG;         /* units per group */
+  int32_t upc;        /* units per CTA */
+  int32_t S;          /* N-tile splits */
+  int64_t brpg;       /* Bm rows per group */
+  int64_t g_base;     int64_t u_base;
+  const float* y;     int64_t ldy;
+  const float* rs;    const float* rb;  int64_t rs_div; int64_t rs_mod;
+  const float* cs;    const float* cb;
+  double* partial;    /* [S * gridX * 128] */
+} adalog_gemm_err_args;
+
+/* returns gridDim.x for the given args (so the caller can size `partial`), or negative on error */
+int adalog_cand_gemm_err_grid(const adalog_gemm_err_args* a);
+int adalog_cand_gemm_err(const adalog_gemm_err_args* a, void* stream);
+
+/* plain (non-candidate) debug GEMM through the same tcgen05 pipeline: D[m,n] FP32 for A [128,ka], Bm [N,ka];
+ * used by the tests to validate descriptors / swizzle / TMEM addressing in isolation. */
+int adalog_debug_gemm_tile(const uint16_t* A, const uint16_t* Bm, int KB, int N, float* D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADALOG_B200_H_ */

@@ -376,6 +376,7 @@ class LinearSearch:
             self.aq = UQ(a_bit)
         else:
             self.aq = LQ(a_bit, shift=torch.tensor([SHIFT_GELU]).to(weight.device))
+            self.aq.q = self.aq.q.to(weight.device)
             self.table = search_table(self.aq.n_levels)
 
     # -- linear.py:111-121
@@ -393,7 +394,7 @@ class LinearSearch:
             yield p0, min(self.eq_n, p0 + self.peq)
 
     # -- linear.py:296-318
-    def eval_w_self(self, cs, cz, topk=1):
+    def sims_w_self(self, cs, cz):
         L = 2 * self.wq.n_levels - 1
         raw = _wview(self.weight, self.n_V).unsqueeze(0)
         sims = []
@@ -402,7 +403,10 @@ class LinearSearch:
             wq = ((raw / s).round_() + z).clamp(0, L)
             wd = (wq - z) * s
             sims.append(torch.mean(_sim(raw, wd), dim=-1, keepdim=False))
-        sims = torch.cat(sims, dim=0)
+        return torch.cat(sims, dim=0)
+
+    def eval_w_self(self, cs, cz, topk=1):
+        sims = self.sims_w_self(cs, cz)
         idx = self.trace.topk(sims, topk, 0, 'w_self').reshape(topk, self.n_V, -1, 1)
         if topk == 1:
             self.wq.scale = torch.gather(cs, 0, idx).squeeze(0)
@@ -410,7 +414,7 @@ class LinearSearch:
         return idx.squeeze(0)
 
     # -- linear.py:320-353
-    def eval_a_self(self, cs, cz, topk=1):
+    def sims_a_self(self, cs, cz):
         L = 2 * self.aq.n_levels - 1
         per_batch = []
         for b0, b1 in self._batches():
@@ -428,7 +432,10 @@ class LinearSearch:
                     sim = torch.mean(sim, dim=1, keepdim=True)
                 parts.append(torch.sum(sim, dim=0, keepdim=True))
             per_batch.append(torch.cat(parts, dim=-1))
-        sims = torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)
+        return torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)
+
+    def eval_a_self(self, cs, cz, topk=1):
+        sims = self.sims_a_self(cs, cz)
         idx = self.trace.topk(sims, topk, -1, 'a_self')
         if topk == 1:
             self.aq.scale = torch.gather(cs, -1, idx).squeeze(-1)
@@ -440,7 +447,7 @@ class LinearSearch:
         return ro.view(*ro.shape[:-1], self.n_V, -1)
 
     # -- linear.py:355-392
-    def eval_w(self, cs, cz, topk=1):
+    def sims_w(self, cs, cz):
         L = 2 * self.wq.n_levels - 1
         per_batch = []
         for b0, b1 in self._batches():
@@ -460,7 +467,10 @@ class LinearSearch:
                     sim = torch.mean(sim, dim=list(range(1, sim.dim() - 3)))
                 parts.append(sim.sum(dim=0, keepdim=True))
             per_batch.append(torch.cat(parts, dim=1))
-        sims = torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)
+        return torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)
+
+    def eval_w(self, cs, cz, topk=1):
+        sims = self.sims_w(cs, cz)
         idx = self.trace.topk(sims, topk, 0, 'w_out').reshape(topk, self.n_V, -1, 1)
         if topk == 1:
             self.wq.scale = torch.gather(cs, 0, idx).squeeze(0)
@@ -487,14 +497,17 @@ class LinearSearch:
         return torch.cat(per_batch, dim=0).sum(dim=0, keepdim=True)
 
     # -- linear.py:394-430
-    def eval_a(self, cs, cz, topk=1):
+    def sims_a(self, cs, cz):
         L = 2 * self.aq.n_levels - 1
 
         def make(x4, p0, p1):
             s, z = cs[:, p0:p1], cz[:, p0:p1]
             xq = ((x4 / s).round_() + z).clamp_(0, L)
             return (xq - z) * s
-        sims = self._a_out_sims(make)
+        return self._a_out_sims(make)
+
+    def eval_a(self, cs, cz, topk=1):
+        sims = self.sims_a(cs, cz)
         idx = self.trace.topk(sims, topk, -1, 'a_out')
         if topk == 1:
             self.aq.scale = torch.gather(cs, -1, idx).squeeze(-1)
@@ -513,10 +526,16 @@ class LinearSearch:
         xs[mask] = 0
         return xs * s - aq.shift
 
+    def sims_log(self, cs, q_cands):
+        """cs None: base-only search at the current scale (linear.py:856-890); else joint (:898-931)"""
+        if cs is None:
+            return self._a_out_sims(lambda x4, p0, p1: self._log_xsim(x4, self.aq.scale, q_cands[:, p0:p1]))
+        return self._a_out_sims(lambda x4, p0, p1: self._log_xsim(x4, cs[:, p0:p1], q_cands[:, p0:p1]))
+
     def eval_log_base(self, q_cands=None, topk=1):
         if q_cands is None:
             q_cands = torch.tensor([i for i in range(10, 11 + self.eq_n)]).to(self.weight.device).view(1, -1)
-        sims = self._a_out_sims(lambda x4, p0, p1: self._log_xsim(x4, self.aq.scale, q_cands[:, p0:p1]))
+        sims = self.sims_log(None, q_cands)
         idx = self.trace.topk(sims, topk, -1, 'log_base')
         if topk == 1:
             self.aq.q = torch.gather(q_cands, -1, idx).view(1)
@@ -524,7 +543,7 @@ class LinearSearch:
         return idx
 
     def eval_scale_logbase(self, cs, q_cands, topk=1):
-        sims = self._a_out_sims(lambda x4, p0, p1: self._log_xsim(x4, cs[:, p0:p1], q_cands[:, p0:p1]))
+        sims = self.sims_log(cs, q_cands)
         idx = self.trace.topk(sims, topk, -1, 'scale_logbase')
         if topk == 1:
             self.aq.scale = torch.gather(cs, -1, idx).squeeze(-1)
@@ -625,6 +644,7 @@ class MatMulSearch:
         self.Bq = UQ(B_bit)
         if post_softmax:
             self.Aq = LQ(A_bit, scale=torch.ones(1, 1, 1, 1).to(A.device))
+            self.Aq.q = self.Aq.q.to(A.device)
             self.Aq.update_table()
             self.table = search_table(self.Aq.n_levels)
         else:
@@ -662,34 +682,37 @@ class MatMulSearch:
         xq = ((x / s).round_() + z).clamp(0, L)
         return (xq - z).mul_(s)
 
+    def sims_A(self, cs, cz):
+        L = 2 * self.Aq.n_levels - 1
+        return self._reduce(lambda A, B, p0, p1: (self._cand_quant(A, cs[p0:p1], cz[p0:p1], L),
+                                                  self.Bq(B).unsqueeze(0)), False).sum(dim=1, keepdim=False)
+
     def eval_A(self, cs, cz, topk=1):
         """matmul.py:135-171."""
-        L = 2 * self.Aq.n_levels - 1
-        sims = self._reduce(lambda A, B, p0, p1: (self._cand_quant(A, cs[p0:p1], cz[p0:p1], L),
-                                                  self.Bq(B).unsqueeze(0)), False).sum(dim=1, keepdim=False)
+        sims = self.sims_A(cs, cz)
         idx = self.trace.topk(sims, topk, 0, 'mm_A').view(topk, 1, -1, 1, 1)
         if topk == 1:
             self.Aq.scale = torch.gather(cs, 0, idx).view(self.Aq.scale.shape)
             self.Aq.zero_point = torch.gather(cz, 0, idx).view(self.Aq.scale.shape).float()
         return idx
 
-    def eval_B(self, cs, cz, topk=1):
-        """matmul.py:173-209."""
+    def sims_B(self, cs, cz):
         L = 2 * self.Bq.n_levels - 1
-        sims = self._reduce(lambda A, B, p0, p1: (self.Aq(A).unsqueeze(0),
+        return self._reduce(lambda A, B, p0, p1: (self.Aq(A).unsqueeze(0),
                                                   self._cand_quant(B, cs[p0:p1], cz[p0:p1], L)),
                             False).sum(dim=1, keepdim=False)
+
+    def eval_B(self, cs, cz, topk=1):
+        """matmul.py:173-209."""
+        sims = self.sims_B(cs, cz)
         idx = self.trace.topk(sims, topk, 0, 'mm_B').view(topk, 1, -1, 1, 1)
         if topk == 1:
             self.Bq.scale = torch.gather(cs, 0, idx).view(self.Bq.scale.shape)
             self.Bq.zero_point = torch.gather(cz, 0, idx).view(self.Bq.scale.shape).float()
         return idx
 
-    def eval_A_log_base(self, q_cands=None, topk=1):
-        """matmul.py:321-358."""
+    def sims_A_log_base(self, q_cands):
         nl = self.Aq.n_levels
-        if q_cands is None:
-            q_cands = torch.tensor([i for i in range(10, 11 + self.eq_n)]).to(self.A.device).view(-1, 1, 1, 1, 1)
 
         def make(A, B, p0, p1):
             qc = q_cands[p0:p1]
@@ -700,7 +723,13 @@ class MatMulSearch:
             a_s = (2 ** (-1 * torch.floor(code * qc / R_BASE))) * self.table.to(A.device)[col]
             a_s[mask] = 0
             return a_s, self.Bq(B).unsqueeze(0)
-        sims = self._reduce(make, True).sum(dim=1, keepdim=True)
+        return self._reduce(make, True).sum(dim=1, keepdim=True)
+
+    def eval_A_log_base(self, q_cands=None, topk=1):
+        """matmul.py:321-358."""
+        if q_cands is None:
+            q_cands = torch.tensor([i for i in range(10, 11 + self.eq_n)]).to(self.A.device).view(-1, 1, 1, 1, 1)
+        sims = self.sims_A_log_base(q_cands)
         idx = self.trace.topk(sims, topk, 0, 'mm_logbase').view(topk, 1, 1, 1, 1)
         if topk == 1:
             self.Aq.q = torch.gather(q_cands, 0, idx).view(1)
@@ -742,8 +771,7 @@ class ConvSearch:
         self.trace = trace or Trace()
         self.wq = UQ(w_bit)
 
-    def eval_w(self, cs, cz, topk=1):
-        """conv.py:226-263 (a_bit >= 8 -> raw FP32 input, conv.py:55-58)."""
+    def sims_w(self, cs, cz):
         L = 2 * self.wq.n_levels - 1
         oc, ic, kw, kh = self.weight.shape
         per_batch = []
@@ -764,19 +792,25 @@ class ConvSearch:
                 sim = torch.mean(_sim(ro, out), [3, 4])
                 parts.append(torch.sum(sim, dim=0, keepdim=True))
             per_batch.append(torch.cat(parts, dim=1))
-        sims = torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)
+        return torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)
+
+    def eval_w(self, cs, cz, topk=1):
+        """conv.py:226-263 (a_bit >= 8 -> raw FP32 input, conv.py:55-58)."""
+        sims = self.sims_w(cs, cz)
         idx = self.trace.topk(sims, topk, 0, 'conv_w').view(topk, -1, 1)
         if topk == 1:
             self.wq.scale = torch.gather(cs, 0, idx).squeeze(dim=0)
             self.wq.zero_point = torch.gather(cz, 0, idx).squeeze(dim=0).float()
         return idx
 
-    def search(self):
-        """conv.py:313-334 with a_bit >= 8: one FPCS round then break (:328-331)."""
+    def init_calib(self):
         self.calib_size = self.raw_input.shape[0]
         numel = 2 * self.raw_input[:self.bs].numel() + 2 * self.raw_out[:self.bs].numel()
         self.peq = chunked_eq_n(self.eq_n, self.memory, numel)
+
+    def search(self):
+        """conv.py:313-334 with a_bit >= 8: one FPCS round then break (:328-331)."""
+        self.init_calib()
         cs, cz = conv_weight_candidates(self.weight, self.wq.n_levels, self.eq_n)
         self.wq.scale, self.wq.zero_point = cs[-2].clone(), cz[-2].clone().float()
-        cs, cz = conv_weight_candidates(self.weight, self.wq.n_levels, self.eq_n)
         fpcs(cs, cz, self.eval_w, 0, self.eq_n, 16, self.steps)
