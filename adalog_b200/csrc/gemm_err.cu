@@ -311,6 +311,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -346,7 +347,7 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
   return 0;
 }
 
-static int validate(const adalog_gemm_err_args* a) {
+static int validate(const adalog_gemm_err_args* a, bool need_partial) {
   ADALOG_REQUIRE(a && a->A && a->Bm, -1, "cand_gemm_err: null operand");
   ADALOG_REQUIRE(a->KB > 0 && a->N > 0 && a->U > 0 && a->UG > 0 && a->upc > 0 && a->S > 0, -1,
                  "cand_gemm_err: non-positive size");
@@ -355,7 +356,7 @@ static int validate(const adalog_gemm_err_args* a) {
   ADALOG_REQUIRE(a->a_rows >= (int64_t)a->U * kBM, -1, "cand_gemm_err: A has fewer than U*128 rows");
   ADALOG_REQUIRE(a->rs_div > 0 && a->rs_mod > 0 && a->rs, -1, "cand_gemm_err: row scale required");
   ADALOG_REQUIRE((a->cs == nullptr) == (a->cb == nullptr), -1, "cand_gemm_err: cs and cb come together");
-  ADALOG_REQUIRE(a->y && a->partial, -1, "cand_gemm_err: y / partial required");
+  ADALOG_REQUIRE(a->y && (a->partial || !need_partial), -1, "cand_gemm_err: y / partial required");
   const int NT = (a->N + a->BN - 1) / a->BN;
   ADALOG_REQUIRE(a->S <= NT, -1, "cand_gemm_err: more N splits than N tiles");
   return 0;
@@ -391,13 +392,13 @@ using namespace adalog;
 extern "C" {
 
 int adalog_cand_gemm_err_grid(const adalog_gemm_err_args* a) {
-  int rc = validate(a);
+  int rc = validate(a, false);
   if (rc) return rc;
   return (a->U / a->UG) * ((a->UG + a->upc - 1) / a->upc);
 }
 
 int adalog_cand_gemm_err(const adalog_gemm_err_args* a, void* stream) {
-  int rc = validate(a);
+  int rc = validate(a, true);
   if (rc) return rc;
   return launch(a, nullptr, (cudaStream_t)stream);
 }
@@ -425,7 +426,7 @@ int adalog_debug_gemm_tile(const uint16_t* A, const uint16_t* Bm, int KB, int N,
   a.U = 1; a.UG = 1; a.upc = 1; a.S = 1; a.brpg = N; a.g_base = 0; a.u_base = 0;
   a.y = zeros; a.ldy = 0; a.rs = ones; a.rb = nullptr; a.rs_div = 1; a.rs_mod = 1; a.cs = nullptr; a.cb = nullptr;
   a.partial = part;
-  int rc = validate(&a);
+  int rc = validate(&a, true);
   if (rc) return rc;
   return launch(&a, D, (cudaStream_t)stream);
 }

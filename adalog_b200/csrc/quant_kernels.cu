@@ -470,9 +470,9 @@ const char* adalog_last_error(void) { return err_buf(); }
 int adalog_uniform_fakequant_f32(const float* x, float* y, int16_t* codes, int64_t n, const float* scale,
                                  const float* zp, int64_t inner, int64_t ngroups, int n_levels, int symmetric,
                                  void* stream) {
-  ADALOG_REQUIRE(x && scale && n >= 0 && inner > 0 && ngroups > 0, -1, "uniform_fakequant: bad arguments");
-  ADALOG_REQUIRE(symmetric || zp, -1, "uniform_fakequant: zp required for the asymmetric form");
   if (n == 0) return 0;
+  ADALOG_REQUIRE(x && scale && n > 0 && inner > 0 && ngroups > 0, -1, "uniform_fakequant: bad arguments");
+  ADALOG_REQUIRE(symmetric || zp, -1, "uniform_fakequant: zp required for the asymmetric form");
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(codes) & 7) == 0;
   const bool vec = aligned && (n % 4 == 0) && (ngroups == 1 || inner % 4 == 0);
@@ -489,7 +489,8 @@ int adalog_uniform_fakequant_f32(const float* x, float* y, int16_t* codes, int64
 int adalog_log_fakequant_f32(const float* x, float* y, int16_t* codes, int64_t n, const float* scale, int kind,
                              int n_levels, const long long* q, const float* table1, const float* table2,
                              const float* shift, int sub_shift, void* stream) {
-  ADALOG_REQUIRE(x && scale && n >= 0 && kind >= 0 && kind <= 2, -1, "log_fakequant: bad arguments");
+  if (n == 0) return 0;
+  ADALOG_REQUIRE(x && scale && n > 0 && kind >= 0 && kind <= 2, -1, "log_fakequant: bad arguments");
   ADALOG_REQUIRE(kind != 2 || (q && table1 && table2), -1, "log_fakequant: adalog needs q/table1/table2");
   ADALOG_REQUIRE(n_levels <= 128, -1, "log_fakequant: n_levels > 128 unsupported");
   if (n == 0) return 0;
@@ -499,8 +500,8 @@ int adalog_log_fakequant_f32(const float* x, float* y, int16_t* codes, int64_t n
 }
 
 int adalog_twin_fakequant_f32(const float* x, float* y, int64_t n, const float* scale2, int n_levels, void* stream) {
-  ADALOG_REQUIRE(x && y && scale2 && n >= 0, -1, "twin_fakequant: bad arguments");
   if (n == 0) return 0;
+  ADALOG_REQUIRE(x && y && scale2 && n > 0, -1, "twin_fakequant: bad arguments");
   twin_fakequant_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, scale2, n_levels);
   return check_launch("twin_fakequant");
 }

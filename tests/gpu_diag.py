@@ -1,0 +1,97 @@
+"""GPU diagnostic (not a pytest file): structural probes of the tcgen05 tile and an early throughput probe.
+Run on the B200 box:  python tests/gpu_diag.py [perf]"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+from adalog_b200 import ops, sweep  # noqa: E402
+
+DEV = 'cuda'
+
+
+def probe_tile():
+    ok = True
+    for ka, N in ((64, 64), (128, 208), (768, 256), (192, 600)):
+        torch.manual_seed(1)
+        A = torch.randint(-15, 16, (128, ka), device=DEV).to(torch.bfloat16)
+        B = torch.randint(-15, 16, (N, ka), device=DEV).to(torch.bfloat16)
+        try:
+            D = ops.debug_gemm_tile(A, B)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f'tile ka={ka} N={N}: EXCEPTION {e}')
+            return False
+        ref = (A.double() @ B.double().t())
+        wrong = (D.double() != ref)
+        print(f'tile ka={ka} N={N}: wrong {wrong.sum().item()} / {wrong.numel()}  maxdiff {(D.double()-ref).abs().max().item()}')
+        if wrong.any():
+            ok = False
+            # K mapping: A one-hot at k = m % ka, B[n,k] = k % 128  -> expect D[m,n] = (m % ka) % 128
+            A1 = torch.zeros(128, ka, device=DEV)
+            A1[torch.arange(128), torch.arange(128) % ka] = 1
+            B1 = (torch.arange(ka, device=DEV) % 128).float().repeat(N, 1)
+            D1 = ops.debug_gemm_tile(A1.to(torch.bfloat16), B1.to(torch.bfloat16))
+            print('  K-map  got', D1[:16, 0].tolist(), ' expect', ((torch.arange(16) % ka) % 128).tolist())
+            print('  K-map  rows 64..72 got', D1[64:72, 0].tolist())
+            # N mapping
+            A2 = torch.zeros(128, ka, device=DEV); A2[:, 0] = 1
+            B2 = torch.zeros(N, ka, device=DEV); B2[:, 0] = (torch.arange(N, device=DEV) % 128).float()
+            D2 = ops.debug_gemm_tile(A2.to(torch.bfloat16), B2.to(torch.bfloat16))
+            print('  N-map  got', D2[0, :24].tolist())
+            print('  N-map  tail got', D2[0, -8:].tolist(), ' expect', (torch.arange(N)[-8:] % 128).tolist())
+            # M mapping
+            A3 = torch.zeros(128, ka, device=DEV); A3[:, 0] = torch.arange(128, device=DEV).float()
+            B3 = torch.zeros(N, ka, device=DEV); B3[:, 0] = 1
+            D3 = ops.debug_gemm_tile(A3.to(torch.bfloat16), B3.to(torch.bfloat16))
+            print('  M-map  got', D3[:8, 0].tolist(), D3[32:36, 0].tolist(), D3[120:, 0].tolist())
+            break
+    return ok
+
+
+def timed(fn, iters=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def perf_probe():
+    from adalog_b200.quantizers import UniformQuantizer
+    import adalog_oracle as O
+    for (Bn, T, D, Do, tag) in ((128, 197, 384, 1152, 'DeiT-S qkv'), (128, 197, 384, 384, 'DeiT-S proj'),
+                                (128, 197, 1536, 384, 'DeiT-S fc2-shaped'), (128, 197, 768, 768, 'DeiT-B proj')):
+        torch.manual_seed(0)
+        x = torch.randn(Bn, T, D, device=DEV)
+        W = torch.randn(Do, D, device=DEV) * 0.02
+        b = torch.zeros(Do, device=DEV)
+        y = torch.nn.functional.linear(x, W, b)
+        ctx = sweep.LinearCtx(x, y, Do)
+        wq, aq = UniformQuantizer(4), UniformQuantizer(4)
+        cs, cz = O.weight_candidates(W, 1, 8, 128)
+        acs, acz = O.activation_candidates(x, 8, 128, False)
+        wq.scale, wq.zero_point = cs[64].clone(), cz[64].clone().float()
+        aq.scale, aq.zero_point = acs[:, 64].clone(), acz[:, 64].clone().float()
+        flops = 2.0 * 128 * Bn * T * D * Do
+        tw = timed(lambda: sweep.linear_err_w(ctx, W.view(1, Do, D), b, aq, cs, cz, 8))
+        ta = timed(lambda: sweep.linear_err_a(ctx, W.view(1, Do, D), b, wq, acs, acz, 8))
+        ts = timed(lambda: sweep.linear_err_a_self(ctx, acs, acz, 8, False))
+        print(f'{tag}: W-sweep {tw:.2f} ms ({flops / tw / 1e9:.0f} TFLOP/s)  A-sweep {ta:.2f} ms '
+              f'({flops / ta / 1e9:.0f} TFLOP/s)  a_self {ts:.2f} ms')
+
+
+if __name__ == '__main__':
+    print(torch.cuda.get_device_name(0))
+    good = probe_tile()
+    print('TILE', 'OK' if good else 'BROKEN')
+    if good and len(sys.argv) > 1 and sys.argv[1] == 'perf':
+        perf_probe()

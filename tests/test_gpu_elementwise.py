@@ -1,0 +1,199 @@
+"""-m gpu: bit-exact parity of the elementwise kernels (fake-quant forwards, operand generators) and 1e-5 parity of
+the self-error sweeps, against the oracle evaluated on the same device and against the committed reference goldens."""
+import pytest
+import torch
+
+import adalog_oracle as O
+from conftest import load_golden
+from gpu_util import assert_sims_close
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _mods():
+    from adalog_b200 import ops, sweep, quantizers
+    return ops, sweep, quantizers
+
+
+def test_quantizer_forward_goldens():
+    """every golden quantizer vector of the reference (CPU) reproduced by the CUDA kernels"""
+    ops, _, Q = _mods()
+    g = load_golden('quantizers')
+    mism_log = 0
+    n_log = 0
+    for c in g['cases']:
+        nl = 2 ** (c['bits'] - 1)
+        x = c['x'].to(DEV)
+        if c['q'] == 'uniform':
+            y = ops.uniform_fakequant(x, c['scale'].to(DEV), c['zero_point'].to(DEV), nl)
+            assert torch.equal(y.cpu(), c['y']), ('uniform', c['bits'], c['tag'])
+        elif c['q'] == 'uniform_sym':
+            y = ops.uniform_fakequant(x, c['scale'].to(DEV), None, nl, sym=True)
+            assert torch.equal(y.cpu(), c['y']), ('uniform_sym', c['bits'])
+        elif c['q'] == 'twin':
+            y = ops.twin_fakequant(x, c['scale'].to(DEV), nl)
+            assert torch.equal(y.cpu(), c['y']), ('twin', c['bits'])
+        else:
+            kind = {'log2': 0, 'shift_log2': 0, 'logsqrt2': 1, 'shift_logsqrt2': 1, 'adalog': 2, 'shift_adalog': 2}[c['q']]
+            kw = {}
+            if kind == 2:
+                kw = dict(q=torch.tensor([c['qv']], device=DEV), table1=c['table1'].to(DEV), table2=c['table2'].to(DEV))
+            shift = c['shift'].to(DEV) if 'shift' in c else None
+            sub = shift is not None and not c.get('reparamed', False)
+            y = ops.log_fakequant(x, c['scale'].to(DEV), kind, nl, shift=shift, sub_shift=sub, **kw)
+            # CPU log2 (goldens) and CUDA log2f may differ in the last ulp exactly at a rounding boundary
+            bad = (y.cpu() != c['y']).sum().item()
+            mism_log += bad
+            n_log += y.numel()
+    print(f'[parity] log-family forwards vs CPU goldens: {mism_log} / {n_log} elements differ')
+    assert mism_log <= 1e-5 * n_log
+
+
+@pytest.mark.parametrize('bits', [3, 4, 6, 8])
+def test_uniform_codes_bit_exact(bits):
+    ops, _, _ = _mods()
+    torch.manual_seed(bits)
+    nl = 2 ** (bits - 1)
+    for shape, sshape in (((64, 197, 192), (1,)), ((3, 64, 192), (3, 64, 1)), ((16, 6, 50, 32), (1, 6, 1, 1)),
+                          ((1000, 77), (77,)), ((5, 7, 13), (1,))):
+        x = (torch.randn(*shape, device=DEV) * 2.0)
+        s = torch.rand(*sshape, device=DEV) * 0.3 + 0.01
+        z = torch.randint(0, 2 * nl, sshape, device=DEV).float()
+        y, codes = ops.uniform_fakequant(x, s, z, nl, want_codes=True)
+        yo, co = O.uniform_fakequant(x, s, z, nl, return_codes=True)
+        assert torch.equal(codes.float(), co), (bits, shape)
+        assert torch.equal(y, yo), (bits, shape)
+
+
+@pytest.mark.parametrize('bits', [3, 4, 6])
+def test_log_codes_bit_exact_same_device(bits):
+    """AdaLog / Log2 / LogSqrt2 codes and dequantised values vs the oracle on the SAME device (torch-CUDA log2)"""
+    ops, _, _ = _mods()
+    torch.manual_seed(10 + bits)
+    nl = 2 ** (bits - 1)
+    p = torch.softmax(torch.randn(8, 6, 197, 197, device=DEV) * 3, dim=-1)
+    p[0, 0, 0, :5] = 0
+    xg = torch.nn.functional.gelu(torch.randn(8, 197, 768, device=DEV) * 1.5)
+    one = torch.ones(1, 1, 1, 1, device=DEV)
+    for qv in (10, 29, 37, 64, 137):
+        t1, t2 = O.adalog_tables(qv, nl)
+        q = torch.tensor([qv], device=DEV)
+        y, c = ops.log_fakequant(p, one, 2, nl, q, t1.to(DEV), t2.to(DEV), want_codes=True)
+        yo, co = O.adalog_fakequant(p, one, q, nl, t1, t2, return_codes=True)
+        assert torch.equal(c.float(), co), ('adalog codes', bits, qv)
+        assert torch.equal(y, yo), ('adalog values', bits, qv)
+        sc = torch.tensor([2.7], device=DEV)
+        sh = torch.tensor([O.SHIFT_GELU], device=DEV)
+        y = ops.log_fakequant(xg, sc, 2, nl, q, t1.to(DEV), t2.to(DEV), shift=sh, sub_shift=True)
+        yo = O.shift_fakequant(O.adalog_fakequant, xg, sh, False, sc, q, nl, t1, t2)
+        assert torch.equal(y, yo), ('shift adalog', bits, qv)
+    for kind, fn in ((0, O.log2_fakequant), (1, O.logsqrt2_fakequant)):
+        y, c = ops.log_fakequant(p, one, kind, nl, want_codes=True)
+        yo, co = fn(p, one, nl, return_codes=True)
+        assert torch.equal(c.float(), co) and torch.equal(y, yo), (kind, bits)
+
+
+def test_module_forwards_cuda():
+    """quantizer nn.Modules on device (the fake-quant forward API), including empty and ragged tensors"""
+    _, _, Q = _mods()
+    q = Q.UniformQuantizer(4, channel_wise=True).to(DEV)
+    q.scale = torch.nn.Parameter(torch.rand(5, 1, device=DEV) * 0.2 + 0.05)
+    q.zero_point = torch.nn.Parameter(torch.randint(0, 16, (5, 1), device=DEV).float())
+    q.inited = True
+    for n in (0, 1, 3, 77):
+        x = torch.randn(5, n, device=DEV)
+        y = q(x)
+        assert y.shape == x.shape
+        if n:
+            assert torch.equal(y, O.uniform_fakequant(x, q.scale.detach(), q.zero_point.detach(), 8))
+    a = Q.ShiftAdaLogQuantizer(4).to(DEV)
+    a.scale = torch.nn.Parameter(torch.tensor([1.9], device=DEV))
+    a.shift.data.fill_(O.SHIFT_GELU)
+    a.q.data.fill_(29)
+    a.update_table()
+    a.inited = True
+    x = torch.nn.functional.gelu(torch.randn(33, 17, device=DEV))
+    yo = O.shift_fakequant(O.adalog_fakequant, x, a.shift.detach(), False, a.scale.detach(), a.q, 8)
+    assert torch.equal(a(x), yo)
+    a.bias_reparamed.data.copy_(torch.tensor(True))
+    yo = O.shift_fakequant(O.adalog_fakequant, x, a.shift.detach(), True, a.scale.detach(), a.q, 8)
+    assert torch.equal(a(x), yo)
+    assert torch.equal(a.codes(x).float(), O.adalog_fakequant(x + a.shift.detach(), a.scale.detach(), a.q, 8,
+                                                             return_codes=True)[1])
+
+
+@pytest.mark.parametrize('bits,n_V,rows,in_f', [(4, 1, 96, 192), (3, 3, 64, 192), (6, 1, 50, 100)])
+def test_sweep_err_w_self(bits, n_V, rows, in_f):
+    ops, sweep, _ = _mods()
+    torch.manual_seed(bits)
+    nl = 2 ** (bits - 1)
+    W = torch.randn(n_V * rows, in_f, device=DEV) * 0.05
+    cs, cz = O.weight_candidates(W, n_V, nl, 128)
+    s = O.LinearSearch(W, None, torch.zeros(1, 1, in_f, device=DEV), torch.zeros(1, 1, n_V * rows, device=DEV), bits,
+                       bits, n_V=n_V)
+    s.init_calib()
+    ref = s.sims_w_self(cs, cz)
+    got = sweep.linear_err_w_self(W.view(n_V, rows, in_f), cs, cz, nl)
+    assert_sims_close(got, ref, 'w_self')
+    # exact ties of the reference stay exact ties (candidates that dequantise identically)
+    tie_ref = ref[0:1] == ref
+    assert torch.equal(tie_ref & (got[0:1] == got), tie_ref)
+
+
+@pytest.mark.parametrize('bits,cw,shape', [(4, False, (32, 197, 192)), (4, True, (32, 197, 192)), (3, True, (16, 50, 96)),
+                                           (6, False, (7, 13, 40)), (4, False, (64, 192)), (4, True, (8, 3, 5, 64))])
+def test_sweep_err_a_self(bits, cw, shape):
+    ops, sweep, _ = _mods()
+    torch.manual_seed(bits)
+    nl = 2 ** (bits - 1)
+    C = shape[-1]
+    x = torch.randn(*shape, device=DEV) * (torch.rand(C, device=DEV) * 2) + 0.3 * torch.randn(C, device=DEV)
+    cs, cz = O.activation_candidates(x, nl, 128, cw)
+    s = O.LinearSearch(torch.zeros(8, C, device=DEV), None, x, torch.zeros(*shape[:-1], 8, device=DEV), bits, bits,
+                       a_channel_wise=cw)
+    s.init_calib()
+    ref = s.sims_a_self(cs, cz)
+    ctx = sweep.LinearCtx(x, torch.zeros(*shape[:-1], 8, device=DEV), 8)
+    got = sweep.linear_err_a_self(ctx, cs, cz, nl, cw)
+    assert_sims_close(got, ref, 'a_self')
+
+
+def test_generators_exact():
+    """bf16 operands hold exactly the integer part of the fake-quantised tensors"""
+    ops, sweep, _ = _mods()
+    torch.manual_seed(0)
+    nl = 8
+    x = torch.randn(37, 100, device=DEV) * 2
+    s = torch.rand(37, device=DEV) * 0.2 + 0.05
+    z = torch.randint(0, 16, (37,), device=DEV).float()
+    out, rowsum = ops.gen_uniform_fixed(x, s, z, 1, 37, nl, want_rowsum=True)
+    ref = (torch.round(x / s[:, None]) + z[:, None]).clamp(0, 15) - z[:, None]
+    assert out.shape == (37, 128) and torch.equal(out[:, :100].float(), ref) and not out[:, 100:].any()
+    assert torch.equal(rowsum, ref.sum(-1))
+    # candidate expansion, per-row candidates laid out [P, R]
+    P = 128
+    cs = torch.rand(P, 37, device=DEV) * 0.2 + 0.05
+    cz = torch.randint(0, 16, (P, 37), device=DEV).float()
+    buf = torch.empty(37 * 128, 128, dtype=torch.bfloat16, device=DEV)
+    rs = torch.empty(37, 128, device=DEV)
+    ops.gen_uniform_cand(x, 0, 37, cs, cz, P, 37, 1, 1, 37, nl, buf, 1, rs)
+    ref = (torch.round(x[:, None, :] / cs.t()[:, :, None]) + cz.t()[:, :, None]).clamp(0, 15) - cz.t()[:, :, None]
+    assert torch.equal(buf.view(37, 128, 128)[:, :, :100].float(), ref)
+    assert torch.equal(rs, ref.sum(-1))
+    # split-3 carries FP32 exactly
+    x3 = ops.gen_split3(x).float().view(37, 3, 128)
+    assert torch.equal(x3.sum(1)[:, :100], x)
+    # log candidate operand vs the search formula
+    p = torch.softmax(torch.randn(20, 50, device=DEV) * 3, -1)
+    qs = torch.arange(10, 138, device=DEV)
+    mt = sweep.search_table_ints(nl, torch.device(DEV))
+    buf = torch.empty(20 * 128, 64, dtype=torch.bfloat16, device=DEV)
+    ops.gen_log_cand(p, 0, 20, None, qs, 128, None, mt, nl, buf)
+    qv = qs.view(1, -1, 1).float()
+    code = torch.round(-p[:, None, :].log2() * 37.0 / qv)
+    mask = code >= 2 * nl
+    code = code.clamp(0, 2 * nl - 1)
+    val = mt[torch.remainder(code * qv, 37.0).round().long()] * 2 ** (-torch.floor(code * qv / 37.0))
+    val[mask] = 0
+    assert torch.equal(buf.view(20, 128, 64)[:, :, :50].float(), val)

@@ -1,0 +1,219 @@
+"""-m gpu: the tcgen05 candidate GEMM (descriptor / swizzle / TMEM plumbing in isolation, then every sweep that is
+built on it) against the oracle on the same device, and whole-layer searches teacher-forced along the oracle's
+trajectory so that every one of the 48/54/45/36/21/6 evaluations is compared on identical candidates."""
+import pytest
+import torch
+
+import adalog_oracle as O
+from conftest import load_golden
+from gpu_util import ForcedTopk, assert_sims_close
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+LINEAR = ['linear_asym_w4a4', 'linear_asym_w3a3_nv3', 'linear_asym_w6a6_chunked', 'linear_head_2d_w4a4',
+          'linear_swin4d_w4a4', 'linear_nobias_w4a4']
+CW = ['linear_cw_reparam_w4a4_nv3', 'linear_cw_reparam_w3a3']
+GELU = ['linear_postgelu_w4a4', 'linear_postgelu_w3a3', 'linear_postgelu_w6a6']
+MATMUL = ['matmul_qk_a4', 'matmul_qk_a3', 'matmul_qk_a6_pooled', 'matmul_pv_s4a4', 'matmul_pv_s3a3', 'matmul_pv_s6a6']
+CONV = ['conv_patch_w4', 'conv_patch_w6']
+
+
+@pytest.mark.parametrize('ka,N', [(64, 16), (64, 64), (128, 208), (256, 256), (768, 300), (192, 1000), (3072, 96)])
+def test_tcgen05_tile_exact(ka, N):
+    """integer-valued bf16 operands: the TMEM accumulator must equal the integer matmul exactly"""
+    from adalog_b200 import ops
+    torch.manual_seed(ka + N)
+    A = torch.randint(-39, 40, (128, ka), device=DEV).to(torch.bfloat16)
+    B = torch.randint(-39, 40, (N, ka), device=DEV).to(torch.bfloat16)
+    D = ops.debug_gemm_tile(A, B)
+    ref = A.double() @ B.double().t()
+    torch.cuda.synchronize()
+    assert torch.equal(D.double(), ref), f'max abs diff {(D.double() - ref).abs().max().item()}'
+
+
+def to_dev(g):
+    return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in g.items()}
+
+
+def build_linear(g, cls, **extra):
+    c = g['cfg']
+    m = cls(c['in_f'], c['out_f'], bias=c['bias'], w_bit=c['w_bit'], a_bit=c['a_bit'], calib_batch_size=c['bs'],
+            eq_n=128, fpcs=True, steps=6, search_round=3, n_V=c['n_V'], **extra).to(DEV)
+    m.weight.data.copy_(g['weight'])
+    if c['bias']:
+        m.bias.data.copy_(g['bias'])
+    return m
+
+
+def oracle_linear(g, **kw):
+    c = g['cfg']
+    return O.LinearSearch(g['weight'].clone(), None if g['bias'] is None else g['bias'].clone(), g['x'].clone(),
+                          g['raw_out'].clone(), c['w_bit'], c['a_bit'], n_V=c['n_V'], calib_batch_size=c['bs'], **kw)
+
+
+@pytest.mark.parametrize('name', LINEAR)
+def test_asym_linear_forced(name):
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    s = oracle_linear(g)
+    s.search_asym()
+    m = build_linear(g, QL.AsymmetricallyBatchingQuantLinear)
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(name)
+    # forced along the oracle's trajectory the stored parameters must be the oracle's, bit for bit
+    assert torch.equal(m.w_quantizer.scale.data, s.wq.scale) and torch.equal(m.w_quantizer.zero_point.data, s.wq.zero_point)
+    assert torch.equal(m.a_quantizer.scale.data, s.aq.scale) and torch.equal(m.a_quantizer.zero_point.data, s.aq.zero_point)
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        out = m(g['x'])
+    ref = torch.nn.functional.linear(s.aq(g['x']), O.quant_weight(s.weight, s.wq, s.n_V), s.bias)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('name', CW)
+def test_channel_wise_forced(name):
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    s = oracle_linear(g, a_channel_wise=True)
+    s.search_channel_wise()
+    lw, lb = s.reparam(g['ln_weight'].clone(), g['ln_bias'].clone())
+    m = build_linear(g, QL.AsymmetricallyChannelWiseBatchingQuantLinear)
+    ln = torch.nn.LayerNorm(g['cfg']['in_f']).to(DEV)
+    ln.weight.data.copy_(g['ln_weight'])
+    ln.bias.data.copy_(g['ln_bias'])
+    m.prev_layer = ln
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+        m.reparam()
+    tap.report(name)
+    assert torch.equal(ln.weight.data, lw) and torch.equal(ln.bias.data, lb)
+    assert torch.equal(m.weight.data, s.weight) and torch.equal(m.bias.data, s.bias)
+    assert torch.equal(m.a_quantizer.scale.data, s.aq.scale) and torch.equal(m.w_quantizer.scale.data, s.wq.scale)
+
+
+@pytest.mark.parametrize('name', GELU)
+def test_postgelu_forced(name):
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    s = oracle_linear(g, a_kind='adalog')
+    s.search_postgelu()
+    m = build_linear(g, QL.PostGeluLogBasedBatchingQuantLinear, quantizer='adalog')
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(name)
+    assert torch.equal(m.a_quantizer.scale.data, s.aq.scale) and torch.equal(m.a_quantizer.q, s.aq.q)
+    assert torch.equal(m.a_quantizer.table1.cpu(), s.aq.table1.cpu()) and torch.equal(m.a_quantizer.table2.cpu(), s.aq.table2.cpu())
+    assert torch.equal(m.w_quantizer.scale.data, s.wq.scale)
+
+
+@pytest.mark.parametrize('name', MATMUL)
+def test_matmul_forced(name):
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    c = g['cfg']
+    ps = 'pv' in name
+    s = O.MatMulSearch(g['A'].clone(), g['B'].clone(), g['raw_out'].clone(), c['A_bit'], c['B_bit'], c['H'],
+                       calib_batch_size=c['bs'], head_channel_wise=c['hcw'], post_softmax=ps)
+    s.search()
+    kw = dict(A_bit=c['A_bit'], B_bit=c['B_bit'], calib_batch_size=c['bs'], search_round=3, eq_n=128,
+              head_channel_wise=c['hcw'], num_heads=c['H'], fpcs=True, steps=6)
+    m = (QL.PostSoftmaxAsymmetricallyBatchingQuantMatMul(quantizer='adalog', **kw) if ps
+         else QL.AsymmetricallyBatchingQuantMatMul(**kw)).to(DEV)
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = [g['A'].clone(), g['B'].clone()], g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(name)
+    assert torch.equal(m.B_quantizer.scale.data, s.Bq.scale) and torch.equal(m.B_quantizer.zero_point.data, s.Bq.zero_point)
+    if ps:
+        assert torch.equal(m.A_quantizer.q, s.Aq.q)
+    else:
+        assert torch.equal(m.A_quantizer.scale.data, s.Aq.scale)
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        assert torch.equal(m(g['A'], g['B']), s.Aq(g['A']) @ s.Bq(g['B']))
+
+
+@pytest.mark.parametrize('name', CONV)
+def test_conv_forced(name):
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    c = g['cfg']
+    s = O.ConvSearch(g['weight'].clone(), g['bias'].clone(), g['x'].clone(), g['raw_out'].clone(), c['w_bit'], c['k'],
+                     calib_batch_size=c['bs'])
+    # torch's default lets cuDNN run this convolution in TF32 (torch.backends.cudnn.allow_tf32=True), i.e. the
+    # reference itself is only ~1e-3 accurate per product on a GPU.  The 1e-5 bar is checked against true FP32.
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        s.search()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    m = QL.AsymmetricallyBatchingQuantConv2d(c['ic'], c['oc'], c['k'], stride=c['k'], w_bit=c['w_bit'], a_bit=8,
+                                             calib_batch_size=c['bs'], search_round=3, eq_n=128, fpcs=True, steps=6).to(DEV)
+    m.weight.data.copy_(g['weight'])
+    m.bias.data.copy_(g['bias'])
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(name)
+    assert torch.equal(m.w_quantizer.scale.data, s.wq.scale) and torch.equal(m.w_quantizer.zero_point.data, s.wq.zero_point)
+
+
+def test_realistic_shapes_sweeps():
+    """DeiT-Tiny-sized layer (192 -> 576, 32x197 tokens): single evaluations at realistic tile counts, incl. ragged
+    N (197) and K (197 -> 256 padding) of the attention matmuls, and exact-tie preservation."""
+    from adalog_b200 import sweep
+    from adalog_b200.quantizers import UniformQuantizer
+    torch.manual_seed(1)
+    Bn, T, D, Do, H = 32, 197, 192, 576, 3
+    x = torch.randn(Bn, T, D, device=DEV) * (torch.rand(D, device=DEV) * 2) + 0.3 * torch.randn(D, device=DEV)
+    W = torch.nn.init.trunc_normal_(torch.empty(Do, D, device=DEV), std=.02)
+    b = torch.randn(Do, device=DEV) * 0.02
+    y = torch.nn.functional.linear(x, W, b)
+    s = O.LinearSearch(W, b, x, y, 4, 4, n_V=3)
+    s.init_calib()
+    cs, cz = O.weight_candidates(W, 3, 8, 128)
+    s.eval_w_self(cs, cz)
+    acs, acz = O.activation_candidates(x, 8, 128, False)
+    s.eval_a_self(acs, acz)
+    wq, aq = UniformQuantizer(4), UniformQuantizer(4)
+    wq.scale, wq.zero_point, aq.scale, aq.zero_point = s.wq.scale, s.wq.zero_point, s.aq.scale, s.aq.zero_point
+    ctx = sweep.LinearCtx(x, y, Do)
+    ref = s.sims_w(cs, cz)
+    got = sweep.linear_err_w(ctx, W.view(3, Do // 3, D), b, aq, cs, cz, 8)
+    assert_sims_close(got, ref, 'linear_err_w 192->576')
+    assert torch.equal((ref[0:1] == ref) & (got[0:1] == got), ref[0:1] == ref), 'exact ties must stay exact'
+    ref = s.sims_a(acs, acz)
+    got = sweep.linear_err_a(ctx, W.view(3, Do // 3, D), b, wq, acs, acz, 8)
+    assert_sims_close(got, ref, 'linear_err_a 192->576')
+    tie = ref[:, 0:1] == ref
+    assert torch.equal(tie & (got[:, 0:1] == got), tie), 'exact ties must stay exact'
+    # attention matmuls
+    q = torch.randn(Bn, H, T, 64, device=DEV)
+    k = torch.randn(Bn, H, 64, T, device=DEV)
+    ms = O.MatMulSearch(q, k, q @ k, 4, 4, H)
+    ms.init_calib()
+    ms._init_from(ms.Aq, q)
+    ms._init_from(ms.Bq, k)
+    mctx = sweep.MatMulCtx(q, k, q @ k)
+    Aq, Bq = UniformQuantizer(4), UniformQuantizer(4)
+    Aq.scale, Aq.zero_point, Bq.scale, Bq.zero_point = ms.Aq.scale, ms.Aq.zero_point, ms.Bq.scale, ms.Bq.zero_point
+    cs, cz = O.matmul_candidates(q, 8, 128, True)
+    assert_sims_close(sweep.matmul_err_A(mctx, Bq, cs, cz, 8, True), ms.sims_A(cs, cz), 'matmul_err_A')
+    cs, cz = O.matmul_candidates(k, 8, 128, True)
+    assert_sims_close(sweep.matmul_err_B(mctx, Aq, cs, cz, 8, True), ms.sims_B(cs, cz), 'matmul_err_B')
+    p = torch.softmax(q @ k * 0.125, dim=-1)
+    v = torch.randn(Bn, H, T, 64, device=DEV)
+    ps = O.MatMulSearch(p, v, p @ v, 4, 4, H, post_softmax=True)
+    ps.init_calib()
+    ps._init_from(ps.Bq, v)
+    pctx = sweep.MatMulCtx(p, v, p @ v)
+    Bq2 = UniformQuantizer(4)
+    Bq2.scale, Bq2.zero_point = ps.Bq.scale, ps.Bq.zero_point
+    qc = torch.arange(10, 138, device=DEV).view(-1, 1, 1, 1, 1)
+    assert_sims_close(sweep.matmul_err_A_log_base(pctx, Bq2, qc, 8), ps.sims_A_log_base(qc), 'matmul_err_A_log_base')
