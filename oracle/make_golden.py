@@ -254,5 +254,79 @@ def main():
     run_conv('conv_patch_w6', torch.randn(8, 3, 16, 16), 3, 12, 4, 6)
 
 
+
+
+# ------------------------------------------------------------------------------------------------ model level
+def install_fake_timm():
+    """Register a minimal `timm` so the reference's utils/wrap_net.py imports: its Attention / WindowAttention
+    classes are the stand-ins of adalog_b200/utils/models.py (timm itself is not installable here)."""
+    import types
+    repo = os.path.dirname(HERE)
+    if repo not in sys.path:
+        sys.path.insert(0, repo)
+    from adalog_b200.utils import models as zoo
+    timm = types.ModuleType('timm')
+    timm.create_model = zoo.create_model
+    tm = types.ModuleType('timm.models')
+    vt = types.ModuleType('timm.models.vision_transformer')
+    vt.Attention, vt.Block = zoo.Attention, zoo.Block
+    st = types.ModuleType('timm.models.swin_transformer')
+    st.WindowAttention, st.SwinTransformerBlock, st.PatchMerging = zoo.WindowAttention, zoo.SwinTransformerBlock, zoo.PatchMerging
+    timm.models, tm.vision_transformer, tm.swin_transformer = tm, vt, st
+    sys.modules.update({'timm': timm, 'timm.models': tm, 'timm.models.vision_transformer': vt,
+                        'timm.models.swin_transformer': st})
+    return zoo
+
+
+def sims_digest(t):
+    import hashlib
+    return hashlib.sha1(t.detach().contiguous().numpy().tobytes()).hexdigest()
+
+
+def run_model(name, model_name, bits, n_img=8, bs=4, img=32):
+    zoo = install_fake_timm()
+    ref_shim.install(16 * 2 ** 30)
+    import importlib
+    wrap_net = importlib.import_module('utils.wrap_net')
+    calibrator = importlib.import_module('utils.calibrator')
+    cfg_mod = importlib.import_module(f'configs.{bits}bit')
+    cfg = cfg_mod.Config()
+    cfg.calib_size, cfg.calib_batch_size = n_img, bs
+    torch.manual_seed(5)
+    model = zoo.create_model(model_name).eval()
+    init_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    images = torch.randn(n_img, 3, img, img)
+    loader = [(images[i:i + bs], torch.zeros(bs, dtype=torch.long)) for i in range(0, n_img, bs)]
+    with torch.no_grad():
+        fp_logits = model(images).clone()
+    model = wrap_net.wrap_modules_in_net(model, cfg, reparam=True)
+    order = [n for n, m in model.named_modules() if hasattr(m, 'calibrated')]
+    with TopkTap() as tap:
+        calibrator.QuantCalibrator(model, loader).batching_quant_calib()
+    model = wrap_net.wrap_reparamed_modules_in_net(model)
+    state_calib = sd(model)
+    with torch.no_grad():
+        logits = model(images).clone()
+    for _, m in model.named_modules():          # test_quant.py:130-133 finish_training
+        if hasattr(m, 'mode') and hasattr(m, 'reparam_bias'):
+            m.reparam_bias()
+    with torch.no_grad():
+        logits_final = model(images).clone()
+    evals = [dict(digest=sims_digest(e['sims']), shape=tuple(e['sims'].shape), k=e['k'], dim=e['dim'], idx=e['idx'].to(torch.int16))
+             for e in tap.evals]
+    save(name, dict(kind='model', model=model_name, bits=bits, n_img=n_img, bs=bs, init_state=init_state, images=images,
+                    order=order, fp_logits=fp_logits, evals=evals, state_calib=state_calib, logits=logits,
+                    state_final=sd(model), logits_final=logits_final, memory=ref_shim._Props.total_memory // 2))
+
+
+def main_models():
+    run_model('model_vit_test_w4a4', 'vit_test_patch8_32', 4)
+    run_model('model_swin_test_w4a4', 'swin_test_patch2_window4_32', 4)
+
+
 if __name__ == '__main__':
-    main()
+    what = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    if what in ('layers', 'all'):
+        main()
+    if what in ('models', 'all'):
+        main_models()
