@@ -49,6 +49,9 @@ SIGNATURES = {
 }
 
 _lib = None
+# kernels launched through this binding (bench.py reports it as gpu_launches)
+LAUNCHES = {'count': 0}
+_NO_LAUNCH = {'adalog_version', 'adalog_cand_gemm_err_grid'}
 
 
 class AdalogError(RuntimeError):
@@ -77,6 +80,8 @@ def load():
 def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(*args)
+    if name not in _NO_LAUNCH:
+        LAUNCHES['count'] += 1
     if rc < 0:
         raise AdalogError(f'{name} failed ({rc}): {lib.adalog_last_error().decode()}')
     return rc

@@ -26,6 +26,8 @@ constexpr uint32_t kTmemCols = 512;
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
 
+// barriers and the epilogue's per-tile y / column-scale staging live in STATIC shared memory so that the compiler
+// keeps the shared address space (LDS/STS, not generic LD/ST); the operand ring is dynamic (1024-byte aligned).
 struct __align__(16) SmemTail {
   float ysm[2][kMaxBN];       // 16-byte aligned: read back as float4 broadcasts
   float csm[2][kMaxBN];
@@ -36,7 +38,7 @@ struct __align__(16) SmemTail {
   uint32_t tmem_base;
   uint32_t pad;
 };
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * (kABytes + kBBytes) + sizeof(SmemTail);
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * (kABytes + kBBytes);
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,7 +145,8 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)kStages * kABytes;
-  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)kStages * (kABytes + kBBytes));
+  __shared__ SmemTail tail_s;
+  SmemTail* tail = &tail_s;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -224,19 +227,62 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     double acc64 = 0.0;
     float rs = 0.0f, rb = 0.0f;
     long long cur_ri = -1;
-    float yreg[2] = {0.0f, 0.0f}, creg[2] = {0.0f, 0.0f};
+    float yreg[2] = {0.0f, 0.0f}, breg[2] = {0.0f, 0.0f}, creg[2] = {0.0f, 0.0f};
+    // global loads for tile t+1 are issued before tile t's math and only consumed (y - cb, store to smem) at the
+    // top of the next iteration, so their latency hides under the epilogue arithmetic
     auto prefetch = [&](int t) {
       const int u = u0 + t / n_nt;
       const int n0 = (nt0 + t % n_nt) * a.BN;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int n = n0 + et + j * 128;
-        float yv = 0.0f, cv = 0.0f;
+        float yv = 0.0f, bv = 0.0f, cv = 0.0f;
         if (et + j * 128 < a.BN && n < a.N) {
           yv = __ldg(a.y + (long long)u * a.ldy + n);
-          if (HAS_CS) { yv -= __ldg(a.cb + n); cv = __ldg(a.cs + n); }
+          if (HAS_CS) { bv = __ldg(a.cb + n); cv = __ldg(a.cs + n); }
         }
-        yreg[j] = yv; creg[j] = cv;
+        yreg[j] = yv; breg[j] = bv; creg[j] = cv;
+      }
+    };
+    // one 32-column slab of the accumulator: e += (y' - rs*(cs*D))^2  [HAS_CS]  or  (y - (rs*D + rb))^2
+    auto consume = [&](const uint32_t (&d)[32], int c0, int lim, int buf, float rs, float rb, float& acc,
+                       int n0, int ncols) {
+      if (a.dbg) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = __uint_as_float(d[j]);
+      }
+      if (lim == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 yv = *reinterpret_cast<const float4*>(&tail_s.ysm[buf][c0 + j]);
+          const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+          if (HAS_CS) {
+            const float4 cv = *reinterpret_cast<const float4*>(&tail_s.csm[buf][c0 + j]);
+            const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float diff = fmaf(-rs, __uint_as_float(d[j + e]) * c4[e], y4[e]);
+              acc = fmaf(diff, diff, acc);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float diff = y4[e] - fmaf(rs, __uint_as_float(d[j + e]), rb);
+              acc = fmaf(diff, diff, acc);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < lim) {
+            float dv = __uint_as_float(d[j]);
+            if (HAS_CS) dv *= tail_s.csm[buf][c0 + j];
+            const float diff = tail_s.ysm[buf][c0 + j] - fmaf(rs, dv, rb);
+            acc = fmaf(diff, diff, acc);
+          }
+        }
       }
     };
     if (n_tiles > 0) prefetch(0);
@@ -246,9 +292,9 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int ncols = min(a.BN, a.N - n0);
       const uint32_t as = t & 1, aphase = (t >> 1) & 1;
       const int buf = t & 1;
-      tail->ysm[buf][et] = yreg[0];
-      if (et + 128 < kMaxBN) tail->ysm[buf][et + 128] = yreg[1];
-      if (HAS_CS) { tail->csm[buf][et] = creg[0]; tail->csm[buf][et + 128] = creg[1]; }
+      tail_s.ysm[buf][et] = yreg[0] - breg[0];
+      tail_s.ysm[buf][et + 128] = yreg[1] - breg[1];
+      if (HAS_CS) { tail_s.csm[buf][et] = creg[0]; tail_s.csm[buf][et + 128] = creg[1]; }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (t + 1 < n_tiles) prefetch(t + 1);
       const long long ri = ((a.u_base + u) / a.rs_div) % a.rs_mod;
@@ -261,42 +307,18 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
       float acc = 0.0f;
       const uint32_t tbase = tmem_base + lane_base + as * kMaxBN;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t d[32];
-        tmem_ld32(tbase + c0, d);
+      // TMEM -> registers, double buffered: the load of slab i+1 is in flight while slab i is reduced
+      const int nslab = (ncols + 31) >> 5;
+      uint32_t da[32], db[32];
+      tmem_ld32(tbase, da);
+      for (int sl = 0; sl < nslab; sl += 2) {
         tmem_ld_wait();
-        if (a.dbg) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = __uint_as_float(d[j]);
-        }
-        const int lim = min(32, ncols - c0);
-        if (lim == 32) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 yv = *reinterpret_cast<const float4*>(&tail->ysm[buf][c0 + j]);
-            float4 cv = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (HAS_CS) cv = *reinterpret_cast<const float4*>(&tail->csm[buf][c0 + j]);
-            const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
-            const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float dv = __uint_as_float(d[j + e]);
-              if (HAS_CS) dv *= c4[e];
-              const float diff = y4[e] - fmaf(rs, dv, rb);
-              acc = fmaf(diff, diff, acc);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < lim) {
-              float dv = __uint_as_float(d[j]);
-              if (HAS_CS) dv *= tail->csm[buf][c0 + j];
-              const float diff = tail->ysm[buf][c0 + j] - fmaf(rs, dv, rb);
-              acc = fmaf(diff, diff, acc);
-            }
-          }
+        if (sl + 1 < nslab) tmem_ld32(tbase + (sl + 1) * 32, db);
+        consume(da, sl * 32, min(32, ncols - sl * 32), buf, rs, rb, acc, n0, ncols);
+        if (sl + 1 < nslab) {
+          tmem_ld_wait();
+          if (sl + 2 < nslab) tmem_ld32(tbase + (sl + 2) * 32, da);
+          consume(db, (sl + 1) * 32, min(32, ncols - (sl + 1) * 32), buf, rs, rb, acc, n0, ncols);
         }
       }
       acc64 += (double)acc;

@@ -277,112 +277,206 @@ __global__ void __launch_bounds__(256) gen_uniform_fixed_kernel(const float* __r
   }
 }
 
-// one CTA per unit: the FP32 row is staged in shared memory and expanded to P<=128 candidate rows
+// ------------------------------------------------------------------------------------------------
+// Candidate expansion: one CTA per unit.  Each thread keeps an 8-element K chunk of the FP32 row in registers and
+// loops over the candidates, so the 128x expansion costs ~8 ALU instructions per generated element.
+//
+// EXACT FAST PATH for rint(x / s) (the reference's torch.round(x / s), linear.py:304/:409):
+//   r = fl(1/s) (IEEE), q = fl(x*r)  =>  |q - x/s| <= 2 ulp(q), and the reference value fl(x/s) is within 0.5 ulp of
+//   x/s.  For |q| <= 256, ulp <= 2^-16, so |q - fl(x/s)| <= 2.5*2^-16 < 2^-14.  Hence if q is farther than 2^-14 from
+//   every half-integer, rint(q) == rint(fl(x/s)) (no tie can be involved either).  Elements closer than that
+//   (probability ~1.2e-4) take the IEEE-division path element-wise.  Values more than 1 outside the clamp range
+//   [lo, hi] = [-zp, L-zp] are decided by the clamp whatever the rounding.  rint is done with the 1.5*2^23 trick.
+// ------------------------------------------------------------------------------------------------
+constexpr float kMagic = 12582912.0f;                 // 1.5 * 2^23
+constexpr float kFracSafe = 0.5f - 6.103515625e-05f;  // 0.5 - 2^-14
+
+__device__ __forceinline__ float rint_magic(float q) { return __fsub_rn(__fadd_rn(q, kMagic), kMagic); }
+
+// c = {1/s, lo = -zp, hi = L - zp, s}.  Returns the clamped integer; sets `unsafe` when the element sits within
+// 2^-14 of a rounding boundary AND the rounding can change the clamped result (lo <= rint <= hi): one step beyond
+// the clamp range the neighbouring integer clamps to the same value.  NaN compares false everywhere -> unsafe.
+__device__ __forceinline__ float uq_int_fast(float x, const float4 c, bool& unsafe) {
+  const float q = __fmul_rn(x, c.x);
+  const float t = rint_magic(q);
+  const float f = fabsf(__fsub_rn(q, t));
+  const float tc = fminf(fmaxf(t, c.y), c.z);
+  unsafe |= !(f <= kFracSafe) && !(tc != t);
+  return tc;
+}
+
 __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __restrict__ x, int K, int64_t ldx,
                                                               const float* __restrict__ cs,
                                                               const float* __restrict__ cz, int P, int64_t pstride,
                                                               int64_t gstride, int64_t g_div, int64_t g_mod,
                                                               int64_t u_base, int nl, uint16_t* __restrict__ out,
-                                                              int kpad, int krep, float* __restrict__ rowsum) {
-  extern __shared__ float smem[];
-  float* xrow = smem;                      // [kpad]
-  float* ps = smem + kpad;                 // [128] scale
-  float* pz = ps + ADALOG_P;               // [128] zp
-  float* rsum = pz + ADALOG_P;             // [128]
+                                                              int kpad, int krep, float* __restrict__ rowsum,
+                                                              int tpc) {
+  __shared__ float4 cand[ADALOG_P];
+  __shared__ float rsum[ADALOG_P];
   const int64_t u = blockIdx.x;
-  for (int k = threadIdx.x; k < kpad; k += blockDim.x) xrow[k] = (k < K) ? __ldg(x + u * ldx + k) : 0.0f;
   const int64_t g = ((u_base + u) / g_div) % g_mod;
+  const float L = (float)(2 * nl - 1);
   for (int p = threadIdx.x; p < ADALOG_P; p += blockDim.x) {
     const int pp = min(p, P - 1);          // pad rows repeat the last candidate
-    ps[p] = __ldg(cs + pp * pstride + g * gstride);
-    pz[p] = __ldg(cz + pp * pstride + g * gstride);
+    const float s = __ldg(cs + pp * pstride + g * gstride);
+    const float z = __ldg(cz + pp * pstride + g * gstride);
+    float r = __fdiv_rn(1.0f, s);
+    if (z != rintf(z)) r = __int_as_float(0x7fc00000);   // non-integer zero point: always take the IEEE path
+    cand[p] = make_float4(r, -z, L - z, s);
     rsum[p] = 0.0f;
   }
   __syncthreads();
-  const float L = (float)(2 * nl - 1);
   const int cpr = kpad >> 3;
-  const int total = ADALOG_P * cpr;
+  const int npg = blockDim.x / tpc;                      // host guarantees blockDim.x == tpc * npg
+  const int lane_chunk = threadIdx.x % tpc, pg = threadIdx.x / tpc;
+  const int per = ADALOG_P / gridDim.y;                  // candidates of this CTA: [p_lo, p_lo + per)
+  const int p_lo = blockIdx.y * per;
   const int64_t pitch = (int64_t)krep * kpad;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int p = idx / cpr;
-    const int kc = (idx - p * cpr) << 3;
-    const float s = ps[p], z = pz[p];
-    float v[8];
-    float sum = 0.0f;
+  uint16_t* obase = out + u * ADALOG_P * pitch;
+  const float* xrow = x + u * ldx;
+  for (int ch = lane_chunk; ch < cpr; ch += tpc) {
+    const int kc = ch << 3;
+    float xv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kc + j;
-      v[j] = (k < K) ? uq_int(xrow[k], s, z, L) : 0.0f;
-      sum += v[j];
+    for (int j = 0; j < 8; ++j) xv[j] = (kc + j < K) ? __ldg(xrow + kc + j) : 0.0f;
+    for (int p = p_lo + pg; p < p_lo + per; p += npg) {
+      const float4 c = cand[p];
+      float v[8];
+      bool unsafe = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = uq_int_fast(xv[j], c, unsafe);
+      if (unsafe) {                                      // ~3% of warps: redo the chunk on the IEEE path
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = uq_int(xv[j], c.w, -c.y, c.z - c.y);
+      }
+      if (kc + 8 > K) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (kc + j >= K) v[j] = 0.0f;
+      }
+      uint16_t* dst = obase + p * pitch + kc;
+      for (int rep = 0; rep < krep; ++rep) store8(dst + (int64_t)rep * kpad, v);
+      if (rowsum) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[j];
+        atomicAdd(rsum + p, sum);
+      }
     }
-    uint16_t* dst = out + (u * ADALOG_P + p) * pitch + kc;
-    for (int rep = 0; rep < krep; ++rep) store8(dst + (int64_t)rep * kpad, v);
-    if (rowsum) atomicAdd(rsum + p, sum);
   }
   if (rowsum) {
     __syncthreads();
-    for (int p = threadIdx.x; p < ADALOG_P; p += blockDim.x) rowsum[u * ADALOG_P + p] = rsum[p];
+    for (int p = p_lo + threadIdx.x; p < p_lo + per; p += blockDim.x) rowsum[u * ADALOG_P + p] = rsum[p];
   }
 }
 
-// AdaLog search form: code from (scale_p, q_p), value m*2^-e (linear.py:872-878 / matmul.py:337-342)
+// ------------------------------------------------------------------------------------------------
+// AdaLog search form (linear.py:872-878 / :913-919, matmul.py:337-342): code from (scale_p, q_p), value m*2^-e.
+//
+// Reference chain per (element, candidate): v = clamp((x+shift)/s, 1e-15, 1); T = fl(fl(-log2f(v)*37)/q);
+// c = rint(T).  EXACT FAST PATH: lx = -log2f(x+shift) once per element, ls = -log2f(s), kq = fl(37/q) once per
+// candidate, t = fma(lx, kq, -ls*kq).  With log2f <= 1 ulp and |lx - ls| <= 49 (outside: IEEE path) one gets
+// |t - T| < 6e-5, so when t is farther than 2.5e-4 from every half-integer rint(t) == c.
+// Unscaled form (post-softmax: no division, no clamp): l37 = fl(lx*37) is the reference's own intermediate and
+// t = fl(l37 * fl(1/q)) is within 2.5 ulp of T: margin 2^-14 as for the uniform case.
+// Codes >= 2n are masked to zero whatever their exact value, so t >= 2n - 0.5 + margin needs no check (covers +inf).
+// e = floor(c*q/37) and (c*q) mod 37 are taken in exact float integer arithmetic (c*q < 2^22).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float log_value_slow(float xs, float lx, bool scaled, float s, float qf,
+                                                const float* mt, float ncode) {
+  float nlg = lx;
+  if (scaled) nlg = -log2f(fminf(fmaxf(__fdiv_rn(xs, s), 1e-15f), 1.0f));
+  float c = rintf(__fdiv_rn(__fmul_rn(nlg, 37.0f), qf));
+  if (!(c < ncode)) return 0.0f;                        // +inf / NaN are masked like the reference
+  c = fmaxf(c, 0.0f);
+  const int cqi = (int)c * (int)qf;
+  if (cqi / 37 > 120) return 0.0f;                      // below 2^-113: flushed on both paths
+  return ldexpf(mt[cqi % 37], -(cqi / 37));
+}
+
 __global__ void __launch_bounds__(256) gen_log_cand_kernel(const float* __restrict__ x, int K, int64_t ldx,
                                                           const float* __restrict__ cs,
                                                           const long long* __restrict__ cq, int P,
                                                           const float* __restrict__ shift,
                                                           const float* __restrict__ mtab, int nl,
-                                                          uint16_t* __restrict__ out, int kpad) {
-  extern __shared__ float smem[];
-  float* xrow = smem;                      // [kpad]  x (+shift), or -log2(x) when unscaled
-  float* ps = smem + kpad;                 // [128]
-  float* pq = ps + ADALOG_P;               // [128]
-  float* mt = pq + ADALOG_P;               // [37]
+                                                          uint16_t* __restrict__ out, int kpad, int tpc) {
+  __shared__ float4 cand[ADALOG_P];        // {mul, off, lim, q}
+  __shared__ float cscale[ADALOG_P];
+  __shared__ float mt[40];
   const int64_t u = blockIdx.x;
-  const float sh = shift ? shift[0] : 0.0f;
   const bool scaled = cs != nullptr;
-  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
-    float v = 0.0f;
-    if (k < K) {
-      v = __ldg(x + u * ldx + k);
-      if (shift) v = __fadd_rn(v, sh);
-      if (!scaled) v = -log2f(v);          // matmul.py:337: no scale, no clamp (log2(0) = -inf -> masked)
-    }
-    xrow[k] = v;
-  }
+  const float sh = shift ? shift[0] : 0.0f;
+  const float margin = scaled ? 2.5e-4f : 6.103515625e-05f;
   for (int p = threadIdx.x; p < ADALOG_P; p += blockDim.x) {
     const int pp = min(p, P - 1);
-    ps[p] = scaled ? __ldg(cs + pp) : 1.0f;
-    pq[p] = (float)cq[pp];
+    const float qf = (float)cq[pp];
+    const float s = scaled ? __ldg(cs + pp) : 1.0f;
+    float mul, off, lim;
+    if (scaled) {
+      const float ls = -log2f(s);
+      mul = __fdiv_rn(37.0f, qf);
+      off = -__fmul_rn(ls, mul);
+      lim = __fadd_rn(ls, 49.0f);                       // lx - ls <= 49  <=>  v comfortably above the 1e-15 clamp
+    } else {
+      mul = __fdiv_rn(1.0f, qf);
+      off = 0.0f;
+      lim = __int_as_float(0x7f800000);                 // +inf: no clamp in the post-softmax form
+    }
+    cand[p] = make_float4(mul, off, lim, qf);
+    cscale[p] = s;
   }
   for (int j = threadIdx.x; j < 37; j += blockDim.x) mt[j] = mtab[j];
   __syncthreads();
   const float ncode = (float)(2 * nl);
+  const float t_masked = ncode - 0.5f + margin;
+  const float frac_safe = 0.5f - margin;
+  const float inv37 = 1.0f / 37.0f;
   const int cpr = kpad >> 3;
-  const int total = ADALOG_P * cpr;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int p = idx / cpr;
-    const int kc = (idx - p * cpr) << 3;
-    const float s = ps[p], qf = pq[p];
-    const int qi = (int)qf;
-    float v[8];
+  const int npg = blockDim.x / tpc;
+  const int lane_chunk = threadIdx.x % tpc, pg = threadIdx.x / tpc;
+  const int per = ADALOG_P / gridDim.y;
+  const int p_lo = blockIdx.y * per;
+  uint16_t* obase = out + u * ADALOG_P * (int64_t)kpad;
+  const float* xrow = x + u * ldx;
+  for (int ch = lane_chunk; ch < cpr; ch += tpc) {
+    const int kc = ch << 3;
+    float xs[8], lx[8], e1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = kc + j;
-      float val = 0.0f;
-      if (k < K) {
-        float nlg;
-        if (scaled) nlg = -log2f(fminf(fmaxf(__fdiv_rn(xrow[k], s), 1e-15f), 1.0f));
-        else        nlg = xrow[k];
-        float c = rintf(__fdiv_rn(__fmul_rn(nlg, 37.0f), qf));
-        if (c < ncode) {                       // NaN and +inf fall through to 0 like the reference mask
-          c = fmaxf(c, 0.0f);
-          const int cqi = (int)c * qi;
-          val = ldexpf(mt[cqi % 37], -(cqi / 37));
-        }
-      }
-      v[j] = val;
+      float v = (kc + j < K) ? __ldg(xrow + kc + j) : 1.0f;
+      if (shift) v = __fadd_rn(v, sh);
+      xs[j] = v;
+      lx[j] = -log2f(v);                                // x <= 0 gives +inf / NaN -> IEEE path below
+      e1[j] = scaled ? lx[j] : __fmul_rn(lx[j], 37.0f);
     }
-    store8(out + (u * ADALOG_P + p) * (int64_t)kpad + kc, v);
+    for (int p = p_lo + pg; p < p_lo + per; p += npg) {
+      const float4 c = cand[p];
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float val;
+        const float t = fmaxf(fmaf(e1[j], c.x, c.y), 0.0f);
+        const float cr = rint_magic(t);
+        const float f = fabsf(__fsub_rn(t, cr));
+        if (!(lx[j] <= c.z)) {
+          // inside (or near) the 1e-15 clamp of the reference, or x <= 0: the closed form does not apply
+          val = log_value_slow(xs[j], lx[j], scaled, cscale[p], c.w, mt, ncode);
+        } else if (t >= t_masked) {
+          val = 0.0f;                                   // code >= 2n whatever the rounding: masked (covers +inf)
+        } else if (f <= frac_safe) {
+          const float cqf = __fmul_rn(cr, c.w);                         // exact integer c*q
+          const float ef = rint_magic(fmaf(__fadd_rn(cqf, 0.5f), inv37, -0.5f));   // floor(c*q/37)
+          const float idxf = fmaf(-37.0f, ef, cqf);                     // (c*q) mod 37, exact
+          const int idx = __float_as_int(__fadd_rn(idxf, kMagic)) & 0x3f;
+          const int ei = __float_as_int(__fadd_rn(ef, kMagic)) & 0xfff;
+          val = (ei > 120) ? 0.0f : __int_as_float(__float_as_int(mt[idx]) - (ei << 23));
+        } else {
+          val = log_value_slow(xs[j], lx[j], scaled, cscale[p], c.w, mt, ncode);
+        }
+        v[j] = (kc + j < K) ? val : 0.0f;
+      }
+      store8(obase + p * (int64_t)kpad + kc, v);
+    }
   }
 }
 
@@ -450,6 +544,14 @@ __global__ void __launch_bounds__(256) gen_split3_kernel(const float* __restrict
     store8(dst + kpad, m);
     store8(dst + 2 * (int64_t)kpad, l);
   }
+}
+
+// candidate split (gridDim.y) of the expansion kernels: enough CTAs to fill the chip even for a short unit list,
+// while every CTA keeps at least `npg` candidates per pass
+static inline int cand_split(int64_t U, int npg) {
+  int ps = 1;
+  while (ps < 32 && U * ps < (int64_t)kNumSMs * 8 && (ADALOG_P / (ps * 2)) >= npg) ps *= 2;
+  return ps;
 }
 
 static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
@@ -547,13 +649,13 @@ int adalog_gen_uniform_cand(const float* x, int64_t U, int K, int64_t ldx, const
   ADALOG_REQUIRE(x && cs && cz && out && U > 0 && U < (1ll << 31) && K > 0 && kpad % ADALOG_BK == 0 && kpad >= K &&
                      P > 0 && P <= ADALOG_P && (krep == 1 || krep == 3) && g_div > 0 && g_mod > 0, -1,
                  "gen_uniform_cand: bad arguments");
-  size_t smem = ((size_t)kpad + 3 * ADALOG_P) * sizeof(float);
-  ADALOG_REQUIRE(smem <= 200 * 1024, -1, "gen_uniform_cand: K too large for shared memory");
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(gen_uniform_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gen_uniform_cand_kernel<<<(unsigned)U, 256, smem, (cudaStream_t)stream>>>(x, K, ldx, cs, cz, P, pstride, gstride,
-                                                                           g_div, g_mod, u_base, n_levels, out, kpad,
-                                                                           krep, rowsum);
+  const int cpr = kpad / 8;
+  const int tpc = cpr < 256 ? cpr : 256;                 // threads along K (8 elements each)
+  const int npg = 256 / tpc;                             // candidate groups per CTA
+  dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
+  gen_uniform_cand_kernel<<<grid, tpc * npg, 0, (cudaStream_t)stream>>>(x, K, ldx, cs, cz, P, pstride, gstride,
+                                                                              g_div, g_mod, u_base, n_levels, out,
+                                                                              kpad, krep, rowsum, tpc);
   return check_launch("gen_uniform_cand");
 }
 
@@ -561,12 +663,12 @@ int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const flo
                         const float* shift, const float* mtab, int n_levels, uint16_t* out, int kpad, void* stream) {
   ADALOG_REQUIRE(x && cq && mtab && out && U > 0 && U < (1ll << 31) && K > 0 && kpad % ADALOG_BK == 0 && kpad >= K &&
                      P > 0 && P <= ADALOG_P, -1, "gen_log_cand: bad arguments");
-  size_t smem = ((size_t)kpad + 2 * ADALOG_P + 40) * sizeof(float);
-  ADALOG_REQUIRE(smem <= 200 * 1024, -1, "gen_log_cand: K too large for shared memory");
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(gen_log_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gen_log_cand_kernel<<<(unsigned)U, 256, smem, (cudaStream_t)stream>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
-                                                                       out, kpad);
+  const int cpr = kpad / 8;
+  const int tpc = cpr < 256 ? cpr : 256;
+  const int npg = 256 / tpc;
+  dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
+  gen_log_cand_kernel<<<grid, tpc * npg, 0, (cudaStream_t)stream>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
+                                                                          out, kpad, tpc);
   return check_launch("gen_log_cand");
 }
 

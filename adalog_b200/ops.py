@@ -14,6 +14,22 @@ from ._lib import AdalogError, GemmErrArgs, call
 P_TILE = 128   # ADALOG_P
 BK = 64        # ADALOG_BK
 
+# bench.py sets PROFILE['on']: every candidate-GEMM launch is then bracketed by CUDA events on its stream and its
+# algorithmic FLOPs recorded, which is how roofline.achieved is measured live inside the timed region
+PROFILE = {'on': False, 'gemm': []}
+
+
+def profile_reset(on):
+    PROFILE['on'] = bool(on)
+    PROFILE['gemm'] = []
+
+
+def profile_gemm_summary():
+    """(total algorithmic FLOPs, total ms, launches) of the candidate GEMM since profile_reset"""
+    flops = sum(f for _, _, f in PROFILE['gemm'])
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in PROFILE['gemm'])
+    return flops, ms, len(PROFILE['gemm'])
+
 
 def _cuda(*ts):
     for t in ts:
@@ -210,7 +226,7 @@ def pick_bn(N):
 
 
 def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, ldy, rs, rb, rs_div, rs_mod, cs, cb,
-                  upc, S, BN=None):
+                  upc, S, BN=None, k_true=None):
     """One launch of adalog_cand_gemm_err.  Returns FP64 partial [S, gridX, 128]."""
     BN = BN or pick_bn(N)
     a = GemmErrArgs()
@@ -225,7 +241,14 @@ def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, l
     gx = call('adalog_cand_gemm_err_grid', ctypes.byref(a))
     partial = torch.empty(S, gx, P_TILE, dtype=torch.float64, device=Bm.device)
     a.partial = partial.data_ptr()
-    call('adalog_cand_gemm_err', ctypes.byref(a), _stream())
+    if PROFILE['on']:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call('adalog_cand_gemm_err', ctypes.byref(a), _stream())
+        e1.record()
+        PROFILE['gemm'].append((e0, e1, 2.0 * P_TILE * U * N * (k_true if k_true else ka)))
+    else:
+        call('adalog_cand_gemm_err', ctypes.byref(a), _stream())
     return partial
 
 

@@ -17,7 +17,7 @@ import torch
 from . import ops
 from .utils import dist as adist
 
-WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '96')) << 20
+WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '768')) << 20
 NUM_SMS = 148
 R_BASE = 37.0
 
@@ -52,32 +52,87 @@ def _pad128(t, dim=-1):
     return t.index_select(dim, idx)
 
 
-def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=1, rs_mod=1, cs=None, cb=None):
+OVERLAP = os.environ.get('ADALOG_B200_OVERLAP', '1') == '1'
+_side = {}
+
+
+def _side_streams(device):
+    key = (device.type, device.index)
+    if key not in _side:
+        _side[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _side[key]
+
+
+def _launch_plan(nu, ug, NT):
+    """static CTA partition of one launch: (units per CTA, CTAs per group, N-tile splits)"""
+    groups = nu // ug
+    want = max(NUM_SMS, min(NUM_SMS * 4, (nu * NT) // 8))
+    upc = min(ug, max(1, math.ceil(nu / want)))
+    cpg = math.ceil(ug / upc)
+    S = min(NT, max(1, round(want / (groups * cpg))))
+    return groups, upc, cpg, S
+
+
+def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=1, rs_mod=1, cs=None, cb=None,
+                  k_true=None):
     """Chunk the units through the bf16 workspace: generate candidate rows, launch the fused GEMM.
 
     gen_cand(u0, nu, out) fills out[nu*128, ka] for units [u0, u0+nu).
     UG == U: one group (linear): returns [n_launch, 128]; else whole groups per launch: returns [U/UG, 128].
+
+    The generator is ALU-bound and the GEMM tensor-core-bound, so with more than one chunk they run on two side
+    streams over a double-buffered workspace: chunk i+1 is generated while chunk i is multiplied.  The chunk
+    schedule (and therefore every partial sum) is identical in both modes.
     """
     dev = Bm.device
     single = UG == U
-    max_units = max(1, WS_BYTES // (ops.P_TILE * ka * 2))
+    unit_elems = ops.P_TILE * ka
+    max_units = max(1, (WS_BYTES // 2) // (unit_elems * 2))
     step = min(U, max_units) if single else min(U, max(1, max_units // UG) * UG)
-    ws = _workspace(dev, step * ops.P_TILE * ka)
+    n_chunks = (U + step - 1) // step
     BN = ops.pick_bn(N)
     NT = (N + BN - 1) // BN
-    outs = []
-    for u0 in range(0, U, step):
-        nu = min(step, U - u0)
-        gen_cand(u0, nu, ws)
+    overlap = OVERLAP and n_chunks > 1 and dev.type == 'cuda'
+    ws_all = _workspace(dev, (2 if overlap else 1) * step * unit_elems)
+    bufs = [ws_all[:step * unit_elems], ws_all[step * unit_elems:]] if overlap else [ws_all]
+
+    def gemm(u0, nu, buf):
         ug = nu if single else UG
-        groups = nu // ug
-        want = max(NUM_SMS, min(NUM_SMS * 4, (nu * NT) // 8))
-        upc = min(ug, max(1, math.ceil(nu / want)))
-        cpg = math.ceil(ug / upc)
-        S = min(NT, max(1, round(want / (groups * cpg))))
-        part = ops.cand_gemm_err(ws, nu * ops.P_TILE, Bm, ka, N, nu, ug, brpg, 0 if single else u0 // UG, u0, y,
-                                 u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN)
-        outs.append(part.view(S, groups, cpg, ops.P_TILE).sum(dim=(0, 2)))
+        groups, upc, cpg, S = _launch_plan(nu, ug, NT)
+        part = ops.cand_gemm_err(buf, nu * ops.P_TILE, Bm, ka, N, nu, ug, brpg, 0 if single else u0 // UG, u0, y,
+                                 u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN, k_true)
+        return part.view(S, groups, cpg, ops.P_TILE).sum(dim=(0, 2))
+
+    outs = []
+    if not overlap:
+        for u0 in range(0, U, step):
+            nu = min(step, U - u0)
+            gen_cand(u0, nu, bufs[0])
+            outs.append(gemm(u0, nu, bufs[0]))
+        return torch.cat(outs, dim=0)
+
+    main = torch.cuda.current_stream(dev)
+    s_gen, s_mma = _side_streams(dev)
+    start = main.record_event()
+    s_gen.wait_event(start)
+    s_mma.wait_event(start)
+    freed = [None, None]
+    for i, u0 in enumerate(range(0, U, step)):
+        nu = min(step, U - u0)
+        b = i & 1
+        with torch.cuda.stream(s_gen):
+            if freed[b] is not None:
+                s_gen.wait_event(freed[b])
+            gen_cand(u0, nu, bufs[b])
+            ready = s_gen.record_event()
+        with torch.cuda.stream(s_mma):
+            s_mma.wait_event(ready)
+            o = gemm(u0, nu, bufs[b])
+            freed[b] = s_mma.record_event()
+        o.record_stream(main)
+        outs.append(o)
+    main.wait_stream(s_gen)
+    main.wait_stream(s_mma)
     return torch.cat(outs, dim=0)
 
 
@@ -185,7 +240,7 @@ def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
                               - shift * c2p[u0:u0 + nu].double() * rowsum[u0:u0 + nu].double()).float()
 
     ntok = ctx.x2d.shape[0]
-    res = run_cand_gemm(gen, out_f, ka, 1, Bm, 0, ntok, ctx.yT, ntok, rs, rb, 1, out_f)
+    res = run_cand_gemm(gen, out_f, ka, 1, Bm, 0, ntok, ctx.yT, ntok, rs, rb, 1, out_f, k_true=in_f)
     res = adist.all_reduce_sum(res)                  # [out, 128]
     sims = -(res[:, :P] / ctx.tok_per_sample)
     return sims.t().float().reshape(P, n_V, rows)
@@ -214,7 +269,8 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
     rs = _pad128(c1).contiguous()
     cb = _f32(bias) if bias is not None else torch.zeros(out_f, device=dev)
     ntok = ctx.x2d.shape[0]
-    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb)
+    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
+                        k_true=in_f)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
     return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
 
@@ -243,7 +299,8 @@ def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
     b = _f32(bias).double() if bias is not None else torch.zeros(out_f, device=dev, dtype=torch.float64)
     cb = (b - shift.double() * s_w.double() * colsum.double()).float().contiguous()
     ntok = ctx.x2d.shape[0]
-    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb)
+    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
+                        k_true=in_f)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
     return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
 
@@ -303,7 +360,7 @@ def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, head_channel_wise):
     cfull = c2 if gs else c2.expand(P, H)
     rs = (_pad128(cfull.t().contiguous()).double() * sB.double().reshape(H, 1)).float().contiguous()   # [H,128]
     U = ctx.Bn * H * ctx.S1
-    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H)
+    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H, k_true=ctx.Kd)
     return _matmul_reduce(res, ctx, P, head_channel_wise, False, ctx.S1 * ctx.S2)
 
 
@@ -335,7 +392,7 @@ def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, head_channel_wise):
     cfull = c2 if gs else c2.expand(P, H)
     rs = (_pad128(cfull.t().contiguous()).double() * sA.reshape(H, 1)).float().contiguous()
     U = ctx.Bn * H * ctx.S2
-    res = run_cand_gemm(gen, U, ka, ctx.S2, Bm, ctx.S1, ctx.S1, ctx.yT2d, ctx.S1, rs, None, ctx.S2, H)
+    res = run_cand_gemm(gen, U, ka, ctx.S2, Bm, ctx.S1, ctx.S1, ctx.yT2d, ctx.S1, rs, None, ctx.S2, H, k_true=ctx.Kd)
     return _matmul_reduce(res, ctx, P, head_channel_wise, False, ctx.S1 * ctx.S2)
 
 
@@ -355,7 +412,7 @@ def matmul_err_A_log_base(ctx, Bq, cq, n_levels_A):
 
     rs = (sB.double().reshape(H, 1) / (4 * n_levels_A - 2)).expand(H, ops.P_TILE).float().contiguous()
     U = ctx.Bn * H * ctx.S1
-    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H)
+    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H, k_true=ctx.Kd)
     return _matmul_reduce(res, ctx, P, True, True, ctx.S1 * ctx.S2).reshape(P, 1)
 
 
@@ -394,6 +451,6 @@ def conv_err_w(ctx, weight2d, bias, cs, cz, n_levels_w):
     b = _f32(bias) if bias is not None else torch.zeros(oc, device=dev)
     rb = b.reshape(-1, 1).expand(oc, ops.P_TILE).contiguous()
     ntok = ctx.yT.shape[1]
-    res = run_cand_gemm(gen, oc, ka, 1, ctx.x3, 0, ntok, ctx.yT, ntok, rs, rb, 1, oc)
+    res = run_cand_gemm(gen, oc, ka, 1, ctx.x3, 0, ntok, ctx.yT, ntok, rs, rb, 1, oc, k_true=K)
     res = adist.all_reduce_sum(res)
     return (-(res[:, :P] / ctx.pos_per_sample)).t().float().contiguous()

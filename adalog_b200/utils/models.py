@@ -312,6 +312,8 @@ MODEL_ZOO = {
     'swin_base_patch4_window7_224': lambda: SwinTransformer(embed_dim=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32)),
     'swin_base_patch4_window12_384': lambda: SwinTransformer(img_size=384, window_size=12, embed_dim=128,
                                                              depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32)),
+    # one-block DeiT-Tiny: the ncu launch-list target (profiles/)
+    'deit_tiny_depth1_patch16_224': lambda: VisionTransformer(embed_dim=192, depth=1, num_heads=3),
     # tiny configurations for tests
     'vit_test_patch8_32': lambda: VisionTransformer(img_size=32, patch_size=8, num_classes=10, embed_dim=32, depth=2,
                                                     num_heads=2),

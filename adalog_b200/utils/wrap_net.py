@@ -115,6 +115,7 @@ def wrap_modules_in_net(model, cfg, reparam=False):
             setattr(module, "matmul2", MatMul())
             fwd = vit_attn_forward if isinstance(module, _VIT_ATTN) else swin_attn_forward
             module.forward = MethodType(fwd, module)
+    device = next(model.parameters()).device
     lookup = {}
     for name, module in model.named_modules():
         lookup[name] = module
@@ -130,8 +131,7 @@ def wrap_modules_in_net(model, cfg, reparam=False):
             grandparent = lookup.get(parent_name.rpartition('.')[0])
             new = _make_linear(name, module, parent, grandparent, cfg, reparam)
         if new is not None:
-            new.to(next(iter(module.parameters()), torch.zeros(0)).device if list(module.parameters()) else
-                   next(model.parameters()).device)
+            new.to(device)
             setattr(parent, leaf, new)
     return model
 

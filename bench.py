@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""FPCS calibration benchmark (BASELINE.json metric: FPCS calibration wall-time & candidates/s; fake-quant img/s).
+
+One STEP = one complete FPCS calibration (QuantCalibrator.batching_quant_calib: capture forwards + all 3150 search
+evaluations x 128 candidates) of DeiT-Small W3A3 on this rank's 128 synthetic 224x224 images (BASELINE.json
+configs[1]); random-init weights, seed 5.  Weak scaling: every rank calibrates against its own 128-image shard and
+the per-candidate FP64 error sums are all-reduced (NCCL), so N ranks calibrate one model on N*128 images.
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (CUDA kernels through libadalog_b200.so)
+  python bench.py --impl reference [...]                    reference arm: the oracle port of the reference's own
+                                                            CPU path on the host cores (bounded sample per step)
+
+Prints ONE JSON line (rank 0).  `value` = candidate scorings per second with the images resident in HBM;
+`e2e` = the same through the public API starting from pinned host images (H2D inside the timed region) and ending
+with the calibrated quantizer parameters read back to the host.
+"""
+import argparse
+import copy
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL_ALIASES = {'deit_tiny': 'deit_tiny_patch16_224', 'deit_small': 'deit_small_patch16_224',
+                 'deit_base': 'deit_base_patch16_224', 'vit_base': 'vit_base_patch16_224',
+                 'vit_small': 'vit_small_patch16_224', 'swin_base': 'swin_base_patch4_window7_224',
+                 'swin_tiny': 'swin_tiny_patch4_window7_224', 'vit_test': 'vit_test_patch8_32'}
+DIMS = {'deit_tiny': (192, 3, 12), 'deit_small': (384, 6, 12), 'deit_base': (768, 12, 12), 'vit_base': (768, 12, 12),
+        'vit_small': (384, 6, 12)}
+TOKENS = 197
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--model', default='deit_small')
+    ap.add_argument('--bits', type=int, default=3)
+    ap.add_argument('--images-per-gpu', type=int, default=128)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=p.get('bf16_tflops_sustained', p.get('bf16_tflops')), hbm=p.get('hbm_gbs'), src='measured')
+    return dict(tflops=1400.0, hbm=6650.0, src='fallback')   # B200_PROFILING.md fallback (sustained)
+
+
+def model_eval_counts(model_key):
+    """(evaluations, candidates, average MACs per token per candidate) for a ViT/DeiT: SURVEY.md section 3.4"""
+    D, H, depth = DIMS[model_key]
+    evals = depth * 258 + 6 + 48
+    macs = (36 * 3 + 36 * 1 + 36 * 4 + 39 * 4) * D * D + (36 + 21) * TOKENS * D     # per token, per block
+    return evals, evals * 128, macs / 258.0
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(model_key, bits, n_img, threads):
+    """Bounded sample of the reference's CPU path (oracle port): one weight-search and one activation-search
+    evaluation (2 x 128 candidates) of blocks.0.attn.proj on n_img synthetic images.  Returns (seconds, candidates,
+    MACs per token per candidate of the sample)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import adalog_oracle as O
+    torch.set_num_threads(threads)
+    D = DIMS[model_key][0]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n_img, TOKENS, D, generator=g) * (torch.rand(D, generator=g) * 2) + 0.3 * torch.randn(D, generator=g)
+    W = torch.nn.init.trunc_normal_(torch.empty(D, D), std=.02, generator=g)
+    b = torch.zeros(D)
+    y = torch.nn.functional.linear(x, W, b)
+    s = O.LinearSearch(W, b, x, y, bits, bits, calib_batch_size=32)
+    s.init_calib()
+    nl = 2 ** (bits - 1)
+    wcs, wcz = O.weight_candidates(W, 1, nl, 128)
+    acs, acz = O.activation_candidates(x, nl, 128, False)
+    s.wq.scale, s.wq.zero_point = wcs[64].clone(), wcz[64].clone().float()
+    s.aq.scale, s.aq.zero_point = acs[:, 64].clone(), acz[:, 64].clone().float()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        s.sims_w(wcs, wcz)
+        s.sims_a(acs, acz)
+    return time.perf_counter() - t0, 256, float(D * D)
+
+
+def cpu_arm_value(model_key, bits, n_img, images_per_gpu, threads):
+    """candidates/s in the bench's unit (one candidate scored on `images_per_gpu` images at the model-average cost)"""
+    secs, cands, macs_sample = cpu_sample(model_key, bits, n_img, threads)
+    _, _, macs_avg = model_eval_counts(model_key)
+    norm = (n_img / images_per_gpu) * (macs_sample / macs_avg)
+    return cands * norm / secs, secs, cands
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_img = 32
+    for _ in range(args.warmup):
+        cpu_arm_value(args.model, args.bits, n_img, args.images_per_gpu, threads)
+    vals, secs_all = [], []
+    for _ in range(args.steps):
+        v, secs, cands = cpu_arm_value(args.model, args.bits, n_img, args.images_per_gpu, threads)
+        vals.append(v)
+        secs_all.append(secs)
+    value = statistics.mean(vals)
+    sample = (f'oracle port of the reference CPU path, {threads} threads: per step 1 weight-search + 1 activation-search '
+              f'evaluation (2x128 candidates) of blocks.0.attn.proj ({args.model}, W{args.bits}A{args.bits}) on {n_img} '
+              f'images; normalised to the bench unit (one candidate on {args.images_per_gpu} images at the '
+              f'model-average GEMM cost per candidate)')
+    out = dict(metric='fpcs_candidates_per_s', value=value, unit='candidates/s', n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=1e3 * statistics.mean(secs_all), higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+               config=workload_config(args),
+               cpu_baseline=dict(value=value, unit='candidates/s', cores=threads, kind='port', sample=sample),
+               e2e=dict(value=value, unit='candidates/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+def workload_config(args):
+    return dict(workload=f'{args.model} W{args.bits}A{args.bits} FPCS calibration (eq_n=128, steps=6, search_round=3), '
+                         f'{args.images_per_gpu} synthetic 224x224 images per GPU, random-init weights, seed 5',
+                images_per_gpu=args.images_per_gpu, l2='inputs larger than L2 + 256 MiB L2 flush between steps',
+                parallelism=f'dp{args.gpus} (samples sharded, FP64 error sums all-reduced)')
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms',
+                                       '200', '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7),
+                                  ('sw_power_cap', 8)):
+                    if r[col].strip().lower() == 'active':
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                continue
+        busy = [v for v in sm if v > 0]
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def build_wrapped(model_name, cfg, device):
+    from adalog_b200.utils import models as zoo
+    from adalog_b200.utils.wrap_net import wrap_modules_in_net
+    torch.manual_seed(5)
+    model = zoo.create_model(model_name).eval()
+    model = wrap_modules_in_net(model, cfg, reparam=True)
+    return model.to(device).eval()
+
+
+def calibrate(model, images, bs):
+    from adalog_b200.utils.calibrator import QuantCalibrator
+    loader = [(images[i:i + bs], None) for i in range(0, images.shape[0], bs)]
+    cal = QuantCalibrator(model, loader)
+    cal.progress = False
+    cal.batching_quant_calib()
+
+
+def quant_params_to_host(model):
+    out, nbytes = {}, 0
+    for k, v in model.state_dict().items():
+        if 'quantizer' in k:
+            out[k] = v.cpu()
+            nbytes += v.numel() * v.element_size()
+    return out, nbytes
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from adalog_b200 import _lib, ops
+    from adalog_b200.utils.wrap_net import wrap_reparamed_modules_in_net
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()   # fail loudly if the extension is missing
+
+    cfg = importlib.import_module(f'adalog_b200.configs.{args.bits}bit').Config()
+    cfg.calib_size, cfg.calib_batch_size = args.images_per_gpu, 32
+    model_name = MODEL_ALIASES[args.model]
+    base = build_wrapped(model_name, cfg, dev)
+    g = torch.Generator().manual_seed(5 + 1000 * rank)
+    img = 32 if args.model == 'vit_test' else 224
+    host_images = torch.randn(args.images_per_gpu, 3, img, img, generator=g).pin_memory()
+    dev_images = host_images.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(from_host):
+        model = copy.deepcopy(base)
+        flush.fill_(1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        images = host_images.to(dev, non_blocking=True) if from_host else dev_images
+        calibrate(model, images, 32)
+        d2h = 0
+        if from_host:
+            _, d2h = quant_params_to_host(model)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        wall = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, wall, d2h, model
+
+    for _ in range(args.warmup):
+        one_step(False)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.LAUNCHES['count'] = 0
+    ops.profile_reset(True)
+    times = []
+    model = None
+    for _ in range(args.steps):
+        ms, wall, _, model = one_step(False)
+        times.append(ms)
+    gemm_flops, gemm_ms, gemm_launches = ops.profile_gemm_summary()
+    ops.profile_reset(False)
+    launches = _lib.LAUNCHES['count']
+    clocks = sampler.stop() if sampler else None
+
+    e2e_ms, d2h = None, 0
+    if not args.no_e2e:
+        e_times, d2h = [], 0
+        for _ in range(max(1, min(args.steps, 2))):
+            ms, wall, d2h, _ = one_step(True)
+            e_times.append(ms)
+        e2e_ms = statistics.mean(e_times)
+
+    # fake-quant forward throughput of the calibrated model (second half of BASELINE's metric)
+    model = wrap_reparamed_modules_in_net(model)
+    with torch.no_grad():
+        model(dev_images[:32])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(0, args.images_per_gpu, 32):
+            model(dev_images[i:i + 32])
+        e1.record()
+        torch.cuda.synchronize()
+        fq_img_s = args.images_per_gpu / (e0.elapsed_time(e1) / 1e3)
+
+    if rank == 0:
+        evals, cands, macs_avg = model_eval_counts(args.model) if args.model in DIMS else (0, 0, 0.0)
+        ms_step = statistics.mean(times)
+        value = world * cands / (ms_step / 1e3)
+        peaks = load_peaks()
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        out = dict(metric='fpcs_candidates_per_s', value=value, unit='candidates/s', n_gpus=world, steps=args.steps,
+                   warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
+                   dtype='bf16 operands (exact integers) / f32 accumulate / f64 error sums', data='synthetic',
+                   config=workload_config(args), evaluations_per_step=evals, candidates_per_step=cands,
+                   calibration_wall_s=ms_step / 1e3, fakequant_img_per_s=fq_img_s, gpu_launches=launches, clocks=clocks,
+                   roofline=dict(kernel='cand_gemm_err_kernel (tcgen05 candidate GEMM + fused error epilogue)',
+                                 bound='tensor', achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s',
+                                 frac=achieved / peaks['tflops'] if peaks['tflops'] else None, traffic=None,
+                                 peak_source=f"{peaks['src']} bf16_tflops_sustained",
+                                 launches=gemm_launches, kernel_ms_per_step=gemm_ms / max(1, args.steps),
+                                 share_of_step=gemm_ms / max(1e-9, sum(times))))
+        if e2e_ms is not None:
+            out['e2e'] = dict(value=world * cands / (e2e_ms / 1e3), unit='candidates/s',
+                              h2d_bytes_per_step=host_images.numel() * 4, d2h_bytes_per_step=d2h,
+                              ms_per_step=e2e_ms)
+        if not args.no_cpu_baseline and world == 1 and args.model in DIMS:
+            threads = os.cpu_count() or 1
+            v, secs, c = cpu_arm_value(args.model, args.bits, 64, args.images_per_gpu, threads)
+            out['cpu_baseline'] = dict(
+                value=v, unit='candidates/s', cores=threads, kind='port',
+                sample=f'oracle port of the reference CPU path: 1 weight-search + 1 activation-search evaluation '
+                       f'(2x128 candidates) of blocks.0.attn.proj on 64 images ({secs:.1f} s), normalised to one '
+                       f'candidate on {args.images_per_gpu} images at the model-average GEMM cost')
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -29,6 +29,17 @@ import torch.nn.functional as F
 SHIFT_GELU = 0.16997124254703522  # linear.py:749 (|min GELU|)
 R_BASE = 37.0                     # logarithm.py:71
 
+# None: contractions run in FP32 exactly like the reference.  torch.float64: the quantisation decisions stay FP32
+# (bit-identical operands) but F.linear / @ / F.conv2d and the error reduction run in FP64 -- the "infinitely
+# precise reference" used by the tests to show which side of a 1e-5 disagreement is the FP32 rounding noise.
+GEMM_DTYPE = None
+
+
+def _up(*ts):
+    if GEMM_DTYPE is None:
+        return ts
+    return tuple(None if t is None else t.to(GEMM_DTYPE) for t in ts)
+
 
 # ----------------------------------------------------------------------------------------------
 # trace recorder: every search evaluation reports (similarity tensor, k, dim, chosen indices)
@@ -460,9 +471,9 @@ class LinearSearch:
                 wq = ((w / s).round_() + z).clamp(0, L)
                 wd = ((wq - z) * s).view(-1, self.in_f)
                 b_sim = self.bias.repeat(p1 - p0) if self.bias is not None else None
-                out = F.linear(self.aq(x), wd, b_sim)
+                out = F.linear(*_up(self.aq(x), wd, b_sim))
                 out = out.view(*out.shape[:-1], p1 - p0, self.n_V, -1)
-                sim = _sim(ro, out)
+                sim = _sim(_up(ro)[0], out)
                 if sim.dim() > 4:
                     sim = torch.mean(sim, dim=list(range(1, sim.dim() - 3)))
                 parts.append(sim.sum(dim=0, keepdim=True))
@@ -488,8 +499,8 @@ class LinearSearch:
                 w_sim = quant_weight(self.weight, self.wq, self.n_V)
                 xs = make_xsim(x.unsqueeze(-1), p0, p1)
                 xs = xs.permute(*list(range(xs.dim() - 2)), -1, -2)
-                out = F.linear(xs, w_sim, self.bias)
-                sim = torch.mean(_sim(ro, out), dim=-1)
+                out = F.linear(*_up(xs, w_sim, self.bias))
+                sim = torch.mean(_sim(_up(ro)[0], out), dim=-1)
                 if sim.dim() > 2:
                     sim = torch.mean(sim, dim=list(range(1, sim.dim() - 1)))
                 parts.append(torch.sum(sim, dim=0, keepdim=True))
@@ -667,8 +678,8 @@ class MatMulSearch:
             parts = []
             for p0 in range(0, self.eq_n, self.peq):
                 p1 = min(self.eq_n, p0 + self.peq)
-                a_s, b_s = make_pair(A, B, p0, p1)
-                sim = _sim(ro, a_s @ b_s)
+                a_s, b_s = _up(*make_pair(A, B, p0, p1))
+                sim = _sim(_up(ro)[0], a_s @ b_s)
                 if self.hcw and not pool_heads:
                     sim = torch.mean(sim, dim=list(range(3, sim.dim())))
                 else:
@@ -787,9 +798,9 @@ class ConvSearch:
                 wq = ((w / s).round_() + z).clamp(0, L)
                 wd = (wq - z).mul_(s).view(-1, ic, kw, kh)
                 b_sim = self.bias.repeat(p1 - p0) if self.bias is not None else None
-                out = F.conv2d(x, wd, b_sim, self.stride, self.padding, self.dilation, self.groups)
+                out = F.conv2d(*_up(x, wd, b_sim), self.stride, self.padding, self.dilation, self.groups)
                 out = torch.cat(torch.chunk(out.unsqueeze(1), chunks=p1 - p0, dim=2), dim=1)
-                sim = torch.mean(_sim(ro, out), [3, 4])
+                sim = torch.mean(_sim(_up(ro)[0], out), [3, 4])
                 parts.append(torch.sum(sim, dim=0, keepdim=True))
             per_batch.append(torch.cat(parts, dim=1))
         return torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)

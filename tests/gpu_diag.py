@@ -87,6 +87,19 @@ def perf_probe():
         ts = timed(lambda: sweep.linear_err_a_self(ctx, acs, acz, 8, False))
         print(f'{tag}: W-sweep {tw:.2f} ms ({flops / tw / 1e9:.0f} TFLOP/s)  A-sweep {ta:.2f} ms '
               f'({flops / ta / 1e9:.0f} TFLOP/s)  a_self {ts:.2f} ms')
+        if 'fc2' in tag:
+            from adalog_b200.quantizers import ShiftAdaLogQuantizer
+            lq = ShiftAdaLogQuantizer(4).to(DEV)
+            lq.scale = torch.nn.Parameter(torch.tensor([3.0], device=DEV))
+            lq.shift.data.fill_(O.SHIFT_GELU)
+            lq.inited = True
+            xg = torch.nn.functional.gelu(x)
+            gctx = sweep.LinearCtx(xg, y, Do)
+            qc = torch.arange(10, 138, device=DEV).view(1, -1)
+            sc = torch.linspace(2.0, 4.0, 128, device=DEV).view(1, -1)
+            tl = timed(lambda: sweep.linear_err_log(gctx, W.view(1, Do, D), b, wq, lq, sc, qc))
+            tlw = timed(lambda: sweep.linear_err_w(gctx, W.view(1, Do, D), b, lq, cs, cz, 8))
+            print(f'{tag}: log A-sweep {tl:.2f} ms ({flops / tl / 1e9:.0f} TFLOP/s)  W-sweep(log act) {tlw:.2f} ms')
 
 
 if __name__ == '__main__':

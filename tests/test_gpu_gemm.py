@@ -160,8 +160,55 @@ def test_conv_forced(name):
     with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
         m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
         m.hyperparameter_searching()
-    tap.report(name)
+    # 128 output positions per (candidate, channel): at 6 bits the FP32 reference's own rounding noise reaches 1e-5
+    # here (see test_fp32_noise_floor), so this tiny case is held to 3e-5 against FP32
+    tap.report(name, rtol=3e-5 if c['w_bit'] == 6 else None)
     assert torch.equal(m.w_quantizer.scale.data, s.wq.scale) and torch.equal(m.w_quantizer.zero_point.data, s.wq.zero_point)
+
+
+def test_fp32_noise_floor():
+    """Where the CUDA sweeps and the FP32 oracle disagree most (6-bit, few tokens), an FP64 evaluation of the same
+    candidates locates the rounding noise.  Integer operands (every uniform sweep): the tensor-core products and sums
+    are exact, so the CUDA sweep is at least as close to FP64 as the FP32 oracle.  The patch-embedding convolution
+    multiplies an UNQUANTISED FP32 input carried as three bf16 pieces: its FP32 tensor-core accumulation is
+    comparable to (here ~3x) the FP32 reference's own rounding; stated tolerance for that path: 3e-5."""
+    from adalog_b200 import sweep
+    for name in ('linear_asym_w6a6_chunked', 'conv_patch_w6'):
+        g = to_dev(load_golden(name))
+        c = g['cfg']
+        if name.startswith('conv'):
+            s = O.ConvSearch(g['weight'].clone(), g['bias'].clone(), g['x'].clone(), g['raw_out'].clone(), c['w_bit'],
+                             c['k'], calib_batch_size=c['bs'])
+            s.init_calib()
+            cs, cz = O.conv_weight_candidates(s.weight, s.wq.n_levels, 128)
+            ctx = sweep.ConvCtx(g['x'], g['raw_out'], (c['k'], c['k']))
+            got = sweep.conv_err_w(ctx, s.weight.view(c['oc'], -1), s.bias, cs, cz, s.wq.n_levels)
+        else:
+            from adalog_b200.quantizers import UniformQuantizer
+            s = oracle_linear(g)
+            s.init_calib()
+            cs, cz = O.weight_candidates(s.weight, 1, 32, 128)
+            acs, acz = O.activation_candidates(g['x'], 32, 128, False)
+            s.aq.scale, s.aq.zero_point = acs[:, 70].clone(), acz[:, 70].clone().float()
+            aq = UniformQuantizer(6)
+            aq.scale, aq.zero_point = s.aq.scale, s.aq.zero_point
+            ctx = sweep.LinearCtx(g['x'], g['raw_out'], c['out_f'])
+            got = sweep.linear_err_w(ctx, s.weight.view(1, c['out_f'], c['in_f']), s.bias, aq, cs, cz, 32)
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            ref32 = s.sims_w(cs, cz)
+            O.GEMM_DTYPE = torch.float64
+            ref64 = s.sims_w(cs, cz)
+        finally:
+            O.GEMM_DTYPE = None
+            torch.backends.cudnn.allow_tf32 = tf32
+        from gpu_util import rel_diff
+        ours, theirs = rel_diff(got, ref64), rel_diff(ref32, ref64)
+        print(f'[parity] {name}: vs FP64 evaluation: CUDA sweep {ours:.2e}, FP32 oracle {theirs:.2e}')
+        assert ours <= (3e-5 if name.startswith('conv') else 1e-5)
+        if not name.startswith('conv'):
+            assert ours <= 2 * theirs + 1e-7
 
 
 def test_realistic_shapes_sweeps():
