@@ -8,6 +8,13 @@ similarity functions.  Nothing here is importable from the product.
 import torch
 
 import adalog_oracle as O
+from adalog_b200.utils import dist as adist
+
+
+def _dp(sims):
+    """similarities are sums over samples: under data parallelism the shards' values add (as the FP64 error sums do
+    in the real sweeps)"""
+    return adist.all_reduce_sum(sims.clone())
 
 
 class Cfg:
@@ -55,27 +62,27 @@ def linear_err_w_self(weight3, cs, cz, n_levels):
 def linear_err_a_self(ctx, cs, cz, n_levels, channel_wise):
     w3 = torch.zeros(1, ctx.raw_out.shape[-1], ctx.raw_input.shape[-1])
     s = _lin(ctx, w3, None, a_bit=_bits(n_levels), cw=channel_wise)
-    return s.sims_a_self(cs, cz)
+    return _dp(s.sims_a_self(cs, cz))
 
 
 def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
     log = getattr(aq, 'is_log', False)
     s = _lin(ctx, weight3, bias, w_bit=_bits(n_levels_w), a_bit=aq.n_bits, a_kind='adalog' if log else 'uniform')
     s.aq = _lq_from(aq) if log else _uq_from(aq)
-    return s.sims_w(cs, cz)
+    return _dp(s.sims_w(cs, cz))
 
 
 def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
     s = _lin(ctx, weight3, bias, w_bit=wq.n_bits, a_bit=_bits(n_levels_a))
     s.wq = _uq_from(wq)
-    return s.sims_a(cs, cz)
+    return _dp(s.sims_a(cs, cz))
 
 
 def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
     s = _lin(ctx, weight3, bias, w_bit=wq.n_bits, a_bit=aq.n_bits, a_kind='adalog')
     s.wq = _uq_from(wq)
     s.aq = _lq_from(aq)
-    return s.sims_log(cs, cq)
+    return _dp(s.sims_log(cs, cq))
 
 
 def _mm(ctx, A_bit, B_bit, hcw, post_softmax=False):
@@ -89,20 +96,20 @@ def _mm(ctx, A_bit, B_bit, hcw, post_softmax=False):
 def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, hcw):
     s = _mm(ctx, _bits(n_levels_A), Bq.n_bits, hcw)
     s.Bq = _uq_from(Bq)
-    return s.sims_A(cs, cz)
+    return _dp(s.sims_A(cs, cz))
 
 
 def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, hcw):
     log = getattr(Aq, 'is_log', False)
     s = _mm(ctx, Aq.n_bits, _bits(n_levels_B), hcw, post_softmax=log)
     s.Aq = _lq_from(Aq) if log else _uq_from(Aq)
-    return s.sims_B(cs, cz)
+    return _dp(s.sims_B(cs, cz))
 
 
 def matmul_err_A_log_base(ctx, Bq, cq, n_levels_A):
     s = _mm(ctx, _bits(n_levels_A), Bq.n_bits, True, post_softmax=True)
     s.Bq = _uq_from(Bq)
-    return s.sims_A_log_base(cq)
+    return _dp(s.sims_A_log_base(cq))
 
 
 class ConvCtx:
@@ -117,7 +124,7 @@ def conv_err_w(ctx, weight2d, bias, cs, cz, n_levels_w):
     s = O.ConvSearch(w4, None if bias is None else bias.detach(), ctx.raw_input, ctx.raw_out, _bits(n_levels_w), k,
                      calib_batch_size=Cfg.bs, memory=Cfg.memory)
     s.init_calib()
-    return s.sims_w(cs, cz)
+    return _dp(s.sims_w(cs, cz))
 
 
 def uniform_fakequant(x, scale, zero_point, n_levels, sym=False, want_codes=False, want_y=True):
