@@ -146,6 +146,34 @@ __global__ void __launch_bounds__(256) twin_fakequant_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Candidate expansion: one CTA per unit.  Each thread keeps an 8-element K chunk of the FP32 row in registers and
+// loops over the candidates, so the 128x expansion costs ~8 ALU instructions per generated element.
+//
+// EXACT FAST PATH for rint(x / s) (the reference's torch.round(x / s), linear.py:304/:409):
+//   r = fl(1/s) (IEEE), q = fl(x*r)  =>  |q - x/s| <= 2 ulp(q), and the reference value fl(x/s) is within 0.5 ulp of
+//   x/s.  For |q| <= 256, ulp <= 2^-16, so |q - fl(x/s)| <= 2.5*2^-16 < 2^-14.  Hence if q is farther than 2^-14 from
+//   every half-integer, rint(q) == rint(fl(x/s)) (no tie can be involved either).  Elements closer than that
+//   (probability ~1.2e-4) take the IEEE-division path element-wise.  Values more than 1 outside the clamp range
+//   [lo, hi] = [-zp, L-zp] are decided by the clamp whatever the rounding.  rint is done with the 1.5*2^23 trick.
+// ------------------------------------------------------------------------------------------------
+constexpr float kMagic = 12582912.0f;                 // 1.5 * 2^23
+constexpr float kFracSafe = 0.5f - 6.103515625e-05f;  // 0.5 - 2^-14
+
+__device__ __forceinline__ float rint_magic(float q) { return __fsub_rn(__fadd_rn(q, kMagic), kMagic); }
+
+// c = {1/s, lo = -zp, hi = L - zp, s}.  Returns the clamped integer; sets `unsafe` when the element sits within
+// 2^-14 of a rounding boundary AND the rounding can change the clamped result (lo <= rint <= hi): one step beyond
+// the clamp range the neighbouring integer clamps to the same value.  NaN compares false everywhere -> unsafe.
+__device__ __forceinline__ float uq_int_fast(float x, const float4 c, bool& unsafe) {
+  const float q = __fmul_rn(x, c.x);
+  const float t = rint_magic(q);
+  const float f = fabsf(__fsub_rn(q, t));
+  const float tc = fminf(fmaxf(t, c.y), c.z);
+  unsafe |= !(f <= kFracSafe) && !(tc != t);
+  return tc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: weight self-error sweep (linear.py:296-309).  One CTA per weight row, one thread per candidate.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) sweep_err_w_self_kernel(const float* __restrict__ W, int R, int K,
@@ -186,7 +214,7 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int p0 = threadIdx.y * 16;
   const bool col_ok = c < Cw;
-  float s[16], z[16];
+  float s[16], z[16], r[16];
   double acc[16];
   float a32[16];
 #pragma unroll
@@ -195,6 +223,7 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
     int64_t ci = per_channel ? ((int64_t)min(c, Cw - 1) * P + p) : p;
     s[j] = __ldg(cs + ci);
     z[j] = __ldg(cz + ci);
+    r[j] = (z[j] == rintf(z[j])) ? __fdiv_rn(1.0f, s[j]) : __int_as_float(0x7fc00000);   // NaN: IEEE path only
     acc[j] = 0.0;
     a32[j] = 0.0f;
   }
@@ -210,7 +239,10 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
       const float xv = __ldg(x + idx);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float d = __fsub_rn(xv, __fmul_rn(uq_int(xv, s[j], z[j], L), s[j]));
+        bool unsafe = false;                              // exact fast path of the generators (same proof)
+        float qi = uq_int_fast(xv, make_float4(r[j], -z[j], L - z[j], s[j]), unsafe);
+        if (unsafe) qi = uq_int(xv, s[j], z[j], L);
+        float d = __fsub_rn(xv, __fmul_rn(qi, s[j]));
         a32[j] = __fadd_rn(a32[j], __fmul_rn(d, d));
       }
     }
@@ -277,41 +309,13 @@ __global__ void __launch_bounds__(256) gen_uniform_fixed_kernel(const float* __r
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Candidate expansion: one CTA per unit.  Each thread keeps an 8-element K chunk of the FP32 row in registers and
-// loops over the candidates, so the 128x expansion costs ~8 ALU instructions per generated element.
-//
-// EXACT FAST PATH for rint(x / s) (the reference's torch.round(x / s), linear.py:304/:409):
-//   r = fl(1/s) (IEEE), q = fl(x*r)  =>  |q - x/s| <= 2 ulp(q), and the reference value fl(x/s) is within 0.5 ulp of
-//   x/s.  For |q| <= 256, ulp <= 2^-16, so |q - fl(x/s)| <= 2.5*2^-16 < 2^-14.  Hence if q is farther than 2^-14 from
-//   every half-integer, rint(q) == rint(fl(x/s)) (no tie can be involved either).  Elements closer than that
-//   (probability ~1.2e-4) take the IEEE-division path element-wise.  Values more than 1 outside the clamp range
-//   [lo, hi] = [-zp, L-zp] are decided by the clamp whatever the rounding.  rint is done with the 1.5*2^23 trick.
-// ------------------------------------------------------------------------------------------------
-constexpr float kMagic = 12582912.0f;                 // 1.5 * 2^23
-constexpr float kFracSafe = 0.5f - 6.103515625e-05f;  // 0.5 - 2^-14
-
-__device__ __forceinline__ float rint_magic(float q) { return __fsub_rn(__fadd_rn(q, kMagic), kMagic); }
-
-// c = {1/s, lo = -zp, hi = L - zp, s}.  Returns the clamped integer; sets `unsafe` when the element sits within
-// 2^-14 of a rounding boundary AND the rounding can change the clamped result (lo <= rint <= hi): one step beyond
-// the clamp range the neighbouring integer clamps to the same value.  NaN compares false everywhere -> unsafe.
-__device__ __forceinline__ float uq_int_fast(float x, const float4 c, bool& unsafe) {
-  const float q = __fmul_rn(x, c.x);
-  const float t = rint_magic(q);
-  const float f = fabsf(__fsub_rn(q, t));
-  const float tc = fminf(fmaxf(t, c.y), c.z);
-  unsafe |= !(f <= kFracSafe) && !(tc != t);
-  return tc;
-}
-
+template <int KREP, bool ROWSUM>
 __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __restrict__ x, int K, int64_t ldx,
                                                               const float* __restrict__ cs,
                                                               const float* __restrict__ cz, int P, int64_t pstride,
                                                               int64_t gstride, int64_t g_div, int64_t g_mod,
                                                               int64_t u_base, int nl, uint16_t* __restrict__ out,
-                                                              int kpad, int krep, float* __restrict__ rowsum,
-                                                              int tpc) {
+                                                              int kpad, float* __restrict__ rowsum, int tpc) {
   __shared__ float4 cand[ADALOG_P];
   __shared__ float rsum[ADALOG_P];
   const int64_t u = blockIdx.x;
@@ -332,16 +336,20 @@ __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __re
   const int lane_chunk = threadIdx.x % tpc, pg = threadIdx.x / tpc;
   const int per = ADALOG_P / gridDim.y;                  // candidates of this CTA: [p_lo, p_lo + per)
   const int p_lo = blockIdx.y * per;
-  const int64_t pitch = (int64_t)krep * kpad;
-  uint16_t* obase = out + u * ADALOG_P * pitch;
+  const int64_t pitch = (int64_t)KREP * kpad;
+  const int64_t dstep = (int64_t)npg * pitch;
+  const int iters = (per - pg + npg - 1) / npg;
   const float* xrow = x + u * ldx;
   for (int ch = lane_chunk; ch < cpr; ch += tpc) {
     const int kc = ch << 3;
+    const bool tail = kc + 8 > K;
     float xv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) xv[j] = (kc + j < K) ? __ldg(xrow + kc + j) : 0.0f;
-    for (int p = p_lo + pg; p < p_lo + per; p += npg) {
-      const float4 c = cand[p];
+    uint16_t* dst = out + (u * ADALOG_P + p_lo + pg) * pitch + kc;
+    const float4* cp = cand + p_lo + pg;
+    for (int it = 0; it < iters; ++it, dst += dstep, cp += npg) {
+      const float4 c = *cp;
       float v[8];
       bool unsafe = false;
 #pragma unroll
@@ -350,21 +358,24 @@ __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = uq_int(xv[j], c.w, -c.y, c.z - c.y);
       }
-      if (kc + 8 > K) {
+      if (tail) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (kc + j >= K) v[j] = 0.0f;
       }
-      uint16_t* dst = obase + p * pitch + kc;
-      for (int rep = 0; rep < krep; ++rep) store8(dst + (int64_t)rep * kpad, v);
-      if (rowsum) {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+#pragma unroll
+      for (int rep = 0; rep < KREP; ++rep) *reinterpret_cast<uint4*>(dst + (int64_t)rep * kpad) = o;
+      if (ROWSUM) {
         float sum = 0.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) sum += v[j];
-        atomicAdd(rsum + p, sum);
+        atomicAdd(rsum + p_lo + pg + it * npg, sum);
       }
     }
   }
-  if (rowsum) {
+  if (ROWSUM) {
     __syncthreads();
     for (int p = p_lo + threadIdx.x; p < p_lo + per; p += blockDim.x) rowsum[u * ADALOG_P + p] = rsum[p];
   }
@@ -375,12 +386,15 @@ __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __re
 //
 // Reference chain per (element, candidate): v = clamp((x+shift)/s, 1e-15, 1); T = fl(fl(-log2f(v)*37)/q);
 // c = rint(T).  EXACT FAST PATH: lx = -log2f(x+shift) once per element, ls = -log2f(s), kq = fl(37/q) once per
-// candidate, t = fma(lx, kq, -ls*kq).  With log2f <= 1 ulp and |lx - ls| <= 49 (outside: IEEE path) one gets
-// |t - T| < 6e-5, so when t is farther than 2.5e-4 from every half-integer rint(t) == c.
+// candidate, t = fma(lx, kq, -ls*kq).  With log2f accurate to 1 ulp and |lx - ls| <= 49 (outside: IEEE path)
+//   |t - T| <= kq*(3.0e-7*|lx| + 3.8e-7*|ls| + 8.6e-8) + 1.8e-7*t        
+// and the check uses twice that bound, evaluated per (element, candidate) with one FFMA:
+//   margin = kq*(6e-7*|lx| + 2e-7) + [kq*7.6e-7*|ls| + 4e-7*2n];  rint(t) == c whenever |t - rint(t)| <= 0.5 - margin.
 // Unscaled form (post-softmax: no division, no clamp): l37 = fl(lx*37) is the reference's own intermediate and
 // t = fl(l37 * fl(1/q)) is within 2.5 ulp of T: margin 2^-14 as for the uniform case.
-// Codes >= 2n are masked to zero whatever their exact value, so t >= 2n - 0.5 + margin needs no check (covers +inf).
-// e = floor(c*q/37) and (c*q) mod 37 are taken in exact float integer arithmetic (c*q < 2^22).
+// An 8-element chunk with any element near a rounding boundary (or in the reference's 1e-15 clamp region) is redone
+// element by element on the IEEE path.  Supported for n_bits <= 6: the numerators m <= 4n-2 = 126 of the dequantised
+// values are then exact in bf16 (8-bit AdaLog would need 9 significant bits; the reference's configs use 3/4/6).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float log_value_slow(float xs, float lx, bool scaled, float s, float qf,
                                                 const float* mt, float ncode) {
@@ -394,88 +408,122 @@ __device__ __forceinline__ float log_value_slow(float xs, float lx, bool scaled,
   return ldexpf(mt[cqi % 37], -(cqi / 37));
 }
 
-__global__ void __launch_bounds__(256) gen_log_cand_kernel(const float* __restrict__ x, int K, int64_t ldx,
-                                                          const float* __restrict__ cs,
-                                                          const long long* __restrict__ cq, int P,
-                                                          const float* __restrict__ shift,
-                                                          const float* __restrict__ mtab, int nl,
-                                                          uint16_t* __restrict__ out, int kpad, int tpc) {
+// The dequantised value of candidate p at code c depends only on (p, c), so each
+// CTA tabulates lut[p][c] = mtab[(c*q_p) % 37] * 2^-floor(c*q_p/37) (0 for c = 2n, the masked code) once and the inner
+// loop is: t (FFMA) -> clamp to [0, 2n] (2 FMNMX) -> rint + code bits (2 FADD) -> boundary check (FADD, FFMA, FSETP)
+// -> one shared load whose address is formed from the magic-number bits.  The profile of the arithmetic version showed
+// the ALU pipe (compares / logic / shifts) at 83% with the FMA pipe at 26%; this version is balanced.
+template <bool SCALED>
+__global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __restrict__ x, int K, int64_t ldx,
+                                                              const float* __restrict__ cs,
+                                                              const long long* __restrict__ cq, int P,
+                                                              const float* __restrict__ shift,
+                                                              const float* __restrict__ mtab, int nl,
+                                                              uint16_t* __restrict__ out, int kpad, int tpc) {
+  extern __shared__ float lut[];           // [per][2n + 1]
   __shared__ float4 cand[ADALOG_P];        // {mul, off, lim, q}
+  __shared__ float chalf[ADALOG_P];        // 0.5 - candidate part of the rounding margin
   __shared__ float cscale[ADALOG_P];
-  __shared__ float mt[40];
+  __shared__ float mt[64];
+  __shared__ float lim_min_s;
   const int64_t u = blockIdx.x;
-  const bool scaled = cs != nullptr;
   const float sh = shift ? shift[0] : 0.0f;
-  const float margin = scaled ? 2.5e-4f : 6.103515625e-05f;
-  for (int p = threadIdx.x; p < ADALOG_P; p += blockDim.x) {
+  const int ncode_i = 2 * nl;
+  const float ncode = (float)ncode_i;
+  const int per = ADALOG_P / gridDim.y;
+  const int p_lo = blockIdx.y * per;
+  for (int j = threadIdx.x; j < 37; j += blockDim.x) mt[j] = mtab[j];
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    const int p = p_lo + i;
     const int pp = min(p, P - 1);
     const float qf = (float)cq[pp];
-    const float s = scaled ? __ldg(cs + pp) : 1.0f;
-    float mul, off, lim;
-    if (scaled) {
+    const float s = SCALED ? __ldg(cs + pp) : 1.0f;
+    float mul, off, lim, hp;
+    if (SCALED) {
       const float ls = -log2f(s);
       mul = __fdiv_rn(37.0f, qf);
       off = -__fmul_rn(ls, mul);
-      lim = __fadd_rn(ls, 49.0f);                       // lx - ls <= 49  <=>  v comfortably above the 1e-15 clamp
+      lim = __fadd_rn(ls, 49.0f);
+      hp = mul * 7.6e-7f * fabsf(ls) + 4e-7f * ncode;
     } else {
       mul = __fdiv_rn(1.0f, qf);
       off = 0.0f;
-      lim = __int_as_float(0x7f800000);                 // +inf: no clamp in the post-softmax form
+      lim = __int_as_float(0x7f800000);
+      hp = 6.103515625e-05f;
     }
     cand[p] = make_float4(mul, off, lim, qf);
+    chalf[p] = 0.5f - hp;
     cscale[p] = s;
   }
-  for (int j = threadIdx.x; j < 37; j += blockDim.x) mt[j] = mtab[j];
   __syncthreads();
-  const float ncode = (float)(2 * nl);
-  const float t_masked = ncode - 0.5f + margin;
-  const float frac_safe = 0.5f - margin;
-  const float inv37 = 1.0f / 37.0f;
+  const int lw = ncode_i + 1;
+  for (int i = threadIdx.x; i < per * lw; i += blockDim.x) {
+    const int pi = i / lw, c = i - pi * lw;
+    float val = 0.0f;
+    if (c < ncode_i) {
+      const int cqi = c * (int)cand[p_lo + pi].w;
+      const int e = cqi / 37;
+      if (e <= 120) val = ldexpf(mt[cqi - e * 37], -e);
+    }
+    lut[i] = val;
+  }
+  if (threadIdx.x == 0) {
+    float m = __int_as_float(0x7f800000);
+    for (int i = 0; i < per; ++i) m = fminf(m, cand[p_lo + i].z);
+    lim_min_s = m;
+  }
+  __syncthreads();
+  const float lim_min = lim_min_s;
   const int cpr = kpad >> 3;
   const int npg = blockDim.x / tpc;
   const int lane_chunk = threadIdx.x % tpc, pg = threadIdx.x / tpc;
-  const int per = ADALOG_P / gridDim.y;
-  const int p_lo = blockIdx.y * per;
-  uint16_t* obase = out + u * ADALOG_P * (int64_t)kpad;
+  const int64_t dstep = (int64_t)npg * kpad;
+  const int iters = (per - pg + npg - 1) / npg;
   const float* xrow = x + u * ldx;
+  // shared address of lut[0][0] minus the magic-number offset: addr = bits(t + 1.5*2^23) * 4 + lut_bias (mod 2^32)
+  const uint32_t lut_bias = (uint32_t)__cvta_generic_to_shared(lut) - 0x2D000000u;
   for (int ch = lane_chunk; ch < cpr; ch += tpc) {
     const int kc = ch << 3;
-    float xs[8], lx[8], e1[8];
+    const bool tail = kc + 8 > K;
+    float xs[8], lx[8], e1[8], gm[8];
+    bool clamp_region = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = (kc + j < K) ? __ldg(xrow + kc + j) : 1.0f;
       if (shift) v = __fadd_rn(v, sh);
       xs[j] = v;
-      lx[j] = -log2f(v);                                // x <= 0 gives +inf / NaN -> IEEE path below
-      e1[j] = scaled ? lx[j] : __fmul_rn(lx[j], 37.0f);
+      lx[j] = -log2f(v);
+      e1[j] = SCALED ? lx[j] : __fmul_rn(lx[j], 37.0f);
+      gm[j] = SCALED ? (6e-7f * fabsf(lx[j]) + 2e-7f) : 0.0f;
+      clamp_region |= !(lx[j] <= lim_min);             // near the reference's 1e-15 clamp, x <= 0 or NaN
     }
-    for (int p = p_lo + pg; p < p_lo + per; p += npg) {
+    uint16_t* dst = out + (u * ADALOG_P + p_lo + pg) * (int64_t)kpad + kc;
+    int p = p_lo + pg;
+    for (int it = 0; it < iters; ++it, dst += dstep, p += npg) {
       const float4 c = cand[p];
+      const float half = chalf[p];
+      const uint32_t row = lut_bias + (uint32_t)((p - p_lo) * lw) * 4u;
       float v[8];
+      bool unsafe = clamp_region;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const float t = fminf(fmaxf(fmaf(e1[j], c.x, c.y), 0.0f), ncode);   // codes >= 2n all read lut[2n] = 0
+        const float tm = __fadd_rn(t, kMagic);
+        const float f = fabsf(__fsub_rn(t, __fsub_rn(tm, kMagic)));
+        unsafe |= !(f <= fmaf(-gm[j], c.x, half));
         float val;
-        const float t = fmaxf(fmaf(e1[j], c.x, c.y), 0.0f);
-        const float cr = rint_magic(t);
-        const float f = fabsf(__fsub_rn(t, cr));
-        if (!(lx[j] <= c.z)) {
-          // inside (or near) the 1e-15 clamp of the reference, or x <= 0: the closed form does not apply
-          val = log_value_slow(xs[j], lx[j], scaled, cscale[p], c.w, mt, ncode);
-        } else if (t >= t_masked) {
-          val = 0.0f;                                   // code >= 2n whatever the rounding: masked (covers +inf)
-        } else if (f <= frac_safe) {
-          const float cqf = __fmul_rn(cr, c.w);                         // exact integer c*q
-          const float ef = rint_magic(fmaf(__fadd_rn(cqf, 0.5f), inv37, -0.5f));   // floor(c*q/37)
-          const float idxf = fmaf(-37.0f, ef, cqf);                     // (c*q) mod 37, exact
-          const int idx = __float_as_int(__fadd_rn(idxf, kMagic)) & 0x3f;
-          const int ei = __float_as_int(__fadd_rn(ef, kMagic)) & 0xfff;
-          val = (ei > 120) ? 0.0f : __int_as_float(__float_as_int(mt[idx]) - (ei << 23));
-        } else {
-          val = log_value_slow(xs[j], lx[j], scaled, cscale[p], c.w, mt, ncode);
-        }
-        v[j] = (kc + j < K) ? val : 0.0f;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(__float_as_uint(tm) * 4u + row));
+        v[j] = val;
       }
-      store8(obase + p * (int64_t)kpad + kc, v);
+      if (unsafe) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = log_value_slow(xs[j], lx[j], SCALED, cscale[p], c.w, mt, ncode);
+      }
+      if (tail) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (kc + j >= K) v[j] = 0.0f;
+      }
+      store8(dst, v);
     }
   }
 }
@@ -653,9 +701,13 @@ int adalog_gen_uniform_cand(const float* x, int64_t U, int K, int64_t ldx, const
   const int tpc = cpr < 256 ? cpr : 256;                 // threads along K (8 elements each)
   const int npg = 256 / tpc;                             // candidate groups per CTA
   dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
-  gen_uniform_cand_kernel<<<grid, tpc * npg, 0, (cudaStream_t)stream>>>(x, K, ldx, cs, cz, P, pstride, gstride,
-                                                                              g_div, g_mod, u_base, n_levels, out,
-                                                                              kpad, krep, rowsum, tpc);
+  cudaStream_t st = (cudaStream_t)stream;
+#define ADALOG_LAUNCH_UCAND(KR, RS)                                                                                  \
+  gen_uniform_cand_kernel<KR, RS><<<grid, tpc * npg, 0, st>>>(x, K, ldx, cs, cz, P, pstride, gstride, g_div, g_mod,  \
+                                                               u_base, n_levels, out, kpad, rowsum, tpc)
+  if (krep == 1) { if (rowsum) ADALOG_LAUNCH_UCAND(1, true); else ADALOG_LAUNCH_UCAND(1, false); }
+  else           { if (rowsum) ADALOG_LAUNCH_UCAND(3, true); else ADALOG_LAUNCH_UCAND(3, false); }
+#undef ADALOG_LAUNCH_UCAND
   return check_launch("gen_uniform_cand");
 }
 
@@ -667,8 +719,15 @@ int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const flo
   const int tpc = cpr < 256 ? cpr : 256;
   const int npg = 256 / tpc;
   dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
-  gen_log_cand_kernel<<<grid, tpc * npg, 0, (cudaStream_t)stream>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
-                                                                          out, kpad, tpc);
+  cudaStream_t st = (cudaStream_t)stream;
+  ADALOG_REQUIRE(2 * n_levels <= 64, -2, "gen_log_cand: AdaLog sweeps support n_bits <= 6 (bf16-exact numerators)");
+  const size_t lut_bytes = (size_t)(ADALOG_P / grid.y) * (2 * n_levels + 1) * sizeof(float);
+  if (cs)
+    gen_log_cand_lut_kernel<true><<<grid, tpc * npg, lut_bytes, st>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
+                                                                      out, kpad, tpc);
+  else
+    gen_log_cand_lut_kernel<false><<<grid, tpc * npg, lut_bytes, st>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
+                                                                       out, kpad, tpc);
   return check_launch("gen_log_cand");
 }
 

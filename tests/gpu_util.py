@@ -53,12 +53,12 @@ class ForcedTopk:
     def __exit__(self, *a):
         torch.topk = self._orig
 
-    def report(self, what, rtol=None):
+    def report(self, what, rtol=None, rtol_by_eval=None):
         worst, flips, bad = 0.0, 0, 0
         assert len(self.got) == len(self.oracle), (len(self.got), len(self.oracle))
         for i, (g, o) in enumerate(zip(self.got, self.oracle)):
             worst = max(worst, assert_sims_close(g['sims'], o['sims'].reshape(g['sims'].shape), f'{what} eval {i}',
-                                                 rtol or RTOL))
+                                                 (rtol_by_eval or {}).get(i, rtol or RTOL)))
             if not torch.equal(g['idx'], o['idx'].reshape(g['idx'].shape)):
                 flips += 1
                 if not near_tie_ok(o['sims'].reshape(g['sims'].shape), o['idx'].reshape(g['idx'].shape), g['idx'],
