@@ -23,8 +23,10 @@ constexpr int kAccStages = 2;
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KiB
 constexpr uint32_t kBBytes = kMaxBN * kBK * 2;     // 32 KiB
 constexpr uint32_t kTmemCols = 512;
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarp0 = 4;            // warps 0-3: TMA producer, MMA issuer + TMEM allocator, two idle
+constexpr int kEpiWarps = 8;            // two epilogue warps per scheduler (TLP hides the FP32 dependent-issue latency)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 384
 
 // barriers and the epilogue's per-tile y / column-scale staging live in STATIC shared memory so that the compiler
 // keeps the shared address space (LDS/STS, not generic LD/ST); the operand ring is dynamic (1024-byte aligned).
@@ -37,6 +39,7 @@ struct __align__(16) SmemTail {
   uint64_t tempty[kAccStages];
   uint32_t tmem_base;
   uint32_t pad;
+  double comb[kBM];           // second epilogue group's sums, folded into the first group's at the end
 };
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * (kABytes + kBBytes);
 
@@ -52,22 +55,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU box
+// bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU box.  try_wait carries a suspend-time
+// hint so a waiting lane sleeps in hardware instead of spinning in the issue slots the epilogue warps need.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s
-      printf("adalog gemm_err: mbarrier timeout (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, parity);
-      __trap();
+    if ((it & 0xff) == 0xff) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) {  // ~2 s
+        printf("adalog gemm_err: mbarrier timeout (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+               threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -138,7 +145,11 @@ struct KArgs {
 };
 
 // ---------------------------------------------------------------- the kernel
-template <bool HAS_CS>
+// MODE_CS: yhat = rs*(cs[n]*D), y' = y - cb[n] (linear A-side sweeps); MODE_RB: yhat = rs*D + rb (W-side sweeps);
+// MODE_PLAIN: yhat = rs*D (attention matmuls)
+enum { MODE_CS = 0, MODE_RB = 1, MODE_PLAIN = 2 };
+
+template <int MODE, bool DEBUG>
 __global__ void __launch_bounds__(kThreads, 1)
 cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -164,7 +175,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], 1); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tail->tfull[i], 1); mbar_init(&tail->tempty[i], 4); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tail->tfull[i], 1); mbar_init(&tail->tempty[i], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
@@ -183,9 +194,11 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t tx = kABytes + (uint32_t)a.BN * kBK * 2;
+      int pu = u0, pcnt = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int u = u0 + t / n_nt;
-        const int nt = nt0 + t % n_nt;
+        const int u = pu;
+        const int nt = nt0 + pcnt;
+        if (++pcnt == n_nt) { pcnt = 0; ++pu; }
         const long long brow = (a.g_base + g_local) * a.brpg + (long long)nt * a.BN;
         for (int kb = 0; kb < a.KB; ++kb) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
@@ -222,112 +235,142 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue: TMEM -> registers -> per-candidate squared error =====================
-    const int et = threadIdx.x - kEpiWarp0 * 32;            // 0..127 = candidate p = TMEM lane
+    // 8 warps: warp w reads TMEM lanes 32*(w%4)..+31 (candidate p = that lane); group eg = (w-4)/4 takes the 32-column
+    // slabs with index == eg (mod 2).  Every candidate therefore has two partial sums, folded in fixed order at the end.
+    constexpr bool HAS_CS = MODE == MODE_CS;
+    const int ew = warp - kEpiWarp0;
+    const int eg = ew >> 2;
+    const int et = ((ew & 3) << 5) | lane;                  // 0..127 = candidate p = TMEM lane
+    const int st = threadIdx.x - kEpiWarp0 * 32;            // 0..255: staging slot (one y column each)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     double acc64 = 0.0;
     float rs = 0.0f, rb = 0.0f;
     long long cur_ri = -1;
-    float yreg[2] = {0.0f, 0.0f}, breg[2] = {0.0f, 0.0f}, creg[2] = {0.0f, 0.0f};
+    float yreg = 0.0f, breg = 0.0f, creg = 0.0f;
     // global loads for tile t+1 are issued before tile t's math and only consumed (y - cb, store to smem) at the
     // top of the next iteration, so their latency hides under the epilogue arithmetic
-    auto prefetch = [&](int t) {
-      const int u = u0 + t / n_nt;
-      const int n0 = (nt0 + t % n_nt) * a.BN;
+    auto prefetch = [&](int u, int n0) {
+      const int n = n0 + st;
+      float yv = 0.0f, bv = 0.0f, cv = 0.0f;
+      if (st < a.BN && n < a.N) {
+        yv = __ldg(a.y + (long long)u * a.ldy + n);
+        if (HAS_CS) { bv = __ldg(a.cb + n); cv = __ldg(a.cs + n); }
+      }
+      yreg = yv; breg = bv; creg = cv;
+    };
+    // four independent accumulators (same instruction sequence for every lane = candidate, so equal candidates still
+    // produce bit-equal sums)
+    float acc4[4];
+    auto quad = [&](const uint32_t (&d)[32], int j, int c0, int buf, float rs, float rb) {
+      const float4 yv = *reinterpret_cast<const float4*>(&tail_s.ysm[buf][c0 + j]);
+      const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+      if (HAS_CS) {
+        const float4 cv = *reinterpret_cast<const float4*>(&tail_s.csm[buf][c0 + j]);
+        const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int n = n0 + et + j * 128;
-        float yv = 0.0f, bv = 0.0f, cv = 0.0f;
-        if (et + j * 128 < a.BN && n < a.N) {
-          yv = __ldg(a.y + (long long)u * a.ldy + n);
-          if (HAS_CS) { bv = __ldg(a.cb + n); cv = __ldg(a.cs + n); }
+        for (int e = 0; e < 4; ++e) {
+          const float diff = fmaf(-rs, __uint_as_float(d[j + e]) * c4[e], y4[e]);
+          acc4[e] = fmaf(diff, diff, acc4[e]);
         }
-        yreg[j] = yv; breg[j] = bv; creg[j] = cv;
+      } else if (MODE == MODE_RB) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float diff = y4[e] - fmaf(rs, __uint_as_float(d[j + e]), rb);
+          acc4[e] = fmaf(diff, diff, acc4[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float diff = fmaf(-rs, __uint_as_float(d[j + e]), y4[e]);
+          acc4[e] = fmaf(diff, diff, acc4[e]);
+        }
       }
     };
-    // one 32-column slab of the accumulator: e += (y' - rs*(cs*D))^2  [HAS_CS]  or  (y - (rs*D + rb))^2
-    auto consume = [&](const uint32_t (&d)[32], int c0, int lim, int buf, float rs, float rb, float& acc,
-                       int n0, int ncols) {
-      if (a.dbg) {
+    // one 32-column slab of the accumulator
+    auto consume = [&](const uint32_t (&d)[32], int c0, int lim, int buf, float rs, float rb, int n0, int ncols) {
+      if (DEBUG) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = __uint_as_float(d[j]);
       }
       if (lim == 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 yv = *reinterpret_cast<const float4*>(&tail_s.ysm[buf][c0 + j]);
-          const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
-          if (HAS_CS) {
-            const float4 cv = *reinterpret_cast<const float4*>(&tail_s.csm[buf][c0 + j]);
-            const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float diff = fmaf(-rs, __uint_as_float(d[j + e]) * c4[e], y4[e]);
-              acc = fmaf(diff, diff, acc);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float diff = y4[e] - fmaf(rs, __uint_as_float(d[j + e]), rb);
-              acc = fmaf(diff, diff, acc);
-            }
-          }
-        }
+        for (int j = 0; j < 32; j += 4) quad(d, j, c0, buf, rs, rb);
       } else {
+        // ragged last slab: whole quads first, then at most three single columns
+        const int lim4 = lim & ~3;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < lim4) quad(d, j, c0, buf, rs, rb);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (j < lim) {
+          if (j >= lim4 && j < lim) {
             float dv = __uint_as_float(d[j]);
             if (HAS_CS) dv *= tail_s.csm[buf][c0 + j];
             const float diff = tail_s.ysm[buf][c0 + j] - fmaf(rs, dv, rb);
-            acc = fmaf(diff, diff, acc);
+            acc4[j & 3] = fmaf(diff, diff, acc4[j & 3]);
           }
         }
       }
     };
-    if (n_tiles > 0) prefetch(0);
+    // incremental work-list position (no per-tile integer division)
+    int cu = u0, cnt = 0;                       // current unit, N tile within the unit
+    long long ri = 0, rrem = 0;                 // row-scale group of `cu`, (u_base + cu) % rs_div
+    if (n_tiles > 0) {
+      const long long gu = a.u_base + cu;
+      ri = (gu / a.rs_div) % a.rs_mod;
+      rrem = gu % a.rs_div;
+      prefetch(cu, (nt0 + cnt) * a.BN);
+    }
     for (int t = 0; t < n_tiles; ++t) {
-      const int u = u0 + t / n_nt;
-      const int n0 = (nt0 + t % n_nt) * a.BN;
+      const int n0 = (nt0 + cnt) * a.BN;
       const int ncols = min(a.BN, a.N - n0);
+      const long long ri_t = ri;
+      // advance to tile t+1
+      if (++cnt == n_nt) {
+        cnt = 0; ++cu;
+        if (++rrem == a.rs_div) { rrem = 0; if (++ri == a.rs_mod) ri = 0; }
+      }
       const uint32_t as = t & 1, aphase = (t >> 1) & 1;
       const int buf = t & 1;
-      tail_s.ysm[buf][et] = yreg[0] - breg[0];
-      tail_s.ysm[buf][et + 128] = yreg[1] - breg[1];
-      if (HAS_CS) { tail_s.csm[buf][et] = creg[0]; tail_s.csm[buf][et + 128] = creg[1]; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (t + 1 < n_tiles) prefetch(t + 1);
-      const long long ri = ((a.u_base + u) / a.rs_div) % a.rs_mod;
-      if (ri != cur_ri) {
-        cur_ri = ri;
-        rs = __ldg(a.rs + ri * kBM + et);
-        rb = a.rb ? __ldg(a.rb + ri * kBM + et) : 0.0f;
+      tail_s.ysm[buf][st] = yreg - breg;
+      if (HAS_CS) tail_s.csm[buf][st] = creg;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (t + 1 < n_tiles) prefetch(cu, (nt0 + cnt) * a.BN);
+      if (ri_t != cur_ri) {
+        cur_ri = ri_t;
+        rs = __ldg(a.rs + ri_t * kBM + et);
+        rb = (MODE == MODE_RB) ? __ldg(a.rb + ri_t * kBM + et) : 0.0f;
       }
       mbar_wait(&tail->tfull[as], aphase);
       tc_fence_after();
-      float acc = 0.0f;
+      acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.0f;
       const uint32_t tbase = tmem_base + lane_base + as * kMaxBN;
-      // TMEM -> registers, double buffered: the load of slab i+1 is in flight while slab i is reduced
+      // this group's slabs eg, eg+2, eg+4, ...; TMEM -> registers double buffered: the load of the next slab is in
+      // flight while the current one is reduced
       const int nslab = (ncols + 31) >> 5;
       uint32_t da[32], db[32];
-      tmem_ld32(tbase, da);
-      for (int sl = 0; sl < nslab; sl += 2) {
+      if (eg < nslab) tmem_ld32(tbase + eg * 32, da);
+      for (int sl = eg; sl < nslab; sl += 4) {
         tmem_ld_wait();
-        if (sl + 1 < nslab) tmem_ld32(tbase + (sl + 1) * 32, db);
-        consume(da, sl * 32, min(32, ncols - sl * 32), buf, rs, rb, acc, n0, ncols);
-        if (sl + 1 < nslab) {
+        if (sl + 2 < nslab) tmem_ld32(tbase + (sl + 2) * 32, db);
+        consume(da, sl * 32, min(32, ncols - sl * 32), buf, rs, rb, n0, ncols);
+        if (sl + 2 < nslab) {
           tmem_ld_wait();
-          if (sl + 2 < nslab) tmem_ld32(tbase + (sl + 2) * 32, da);
-          consume(db, (sl + 1) * 32, min(32, ncols - (sl + 1) * 32), buf, rs, rb, acc, n0, ncols);
+          if (sl + 4 < nslab) tmem_ld32(tbase + (sl + 4) * 32, da);
+          consume(db, (sl + 2) * 32, min(32, ncols - (sl + 2) * 32), buf, rs, rb, n0, ncols);
         }
       }
-      acc64 += (double)acc;
+      acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tempty[as]);
     }
-    if (a.partial)
-      a.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * kBM + et] = acc64;
+    // fold the two column groups in fixed order: (group 0) + (group 1)
+    if (eg == 1) tail_s.comb[et] = acc64;
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    if (eg == 0 && a.partial)
+      a.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * kBM + et] = acc64 + tail_s.comb[et];
   }
 
   tc_fence_before();
@@ -397,13 +440,17 @@ static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st) {
   rc = make_map(&tmB, a->Bm, a->b_rows, (int64_t)a->KB * kBK, a->BN);
   if (rc) return rc;
   dim3 grid((unsigned)((a->U / a->UG) * k.cpg), (unsigned)a->S);
-  if (a->cs) {
-    cudaFuncSetAttribute(cand_gemm_err_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    cand_gemm_err_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);
-  } else {
-    cudaFuncSetAttribute(cand_gemm_err_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    cand_gemm_err_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);
-  }
+#define ADALOG_LAUNCH_GEMM(MD, DBG)                                                                           \
+  do {                                                                                                        \
+    cudaFuncSetAttribute(cand_gemm_err_kernel<MD, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                         (int)kSmemBytes);                                                                    \
+    cand_gemm_err_kernel<MD, DBG><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);                           \
+  } while (0)
+  if (dbg)         ADALOG_LAUNCH_GEMM(MODE_PLAIN, true);
+  else if (a->cs)  ADALOG_LAUNCH_GEMM(MODE_CS, false);
+  else if (a->rb)  ADALOG_LAUNCH_GEMM(MODE_RB, false);
+  else             ADALOG_LAUNCH_GEMM(MODE_PLAIN, false);
+#undef ADALOG_LAUNCH_GEMM
   return check_launch("cand_gemm_err");
 }
 

@@ -102,9 +102,50 @@ def perf_probe():
             print(f'{tag}: log A-sweep {tl:.2f} ms ({flops / tl / 1e9:.0f} TFLOP/s)  W-sweep(log act) {tlw:.2f} ms')
 
 
+def perf_matmul():
+    from adalog_b200.quantizers import UniformQuantizer
+    import adalog_oracle as O
+    Bn, H, T, dh = 128, 6, 197, 64
+    torch.manual_seed(0)
+    q = torch.randn(Bn, H, T, dh, device=DEV)
+    k = torch.randn(Bn, H, dh, T, device=DEV)
+    out = q @ k
+    ctx = sweep.MatMulCtx(q, k, out)
+    cs, cz = O.matmul_candidates(q, 4, 128, True)
+    Aq, Bq = UniformQuantizer(3), UniformQuantizer(3)
+    Aq.scale, Aq.zero_point = cs[64].clone(), cz[64].clone().float()
+    Bq.scale, Bq.zero_point = cs[64].clone(), cz[64].clone().float()
+    p = torch.softmax(out * 0.125, -1)
+    v = torch.randn(Bn, H, T, dh, device=DEV)
+    pctx = sweep.MatMulCtx(p, v, p @ v)
+    qc = torch.arange(10, 138, device=DEV).view(-1, 1, 1, 1, 1)
+    for tag, fn in (('QK A-sweep', lambda: sweep.matmul_err_A(ctx, Bq, cs, cz, 4, True)),
+                    ('QK B-sweep', lambda: sweep.matmul_err_B(ctx, Aq, cs, cz, 4, True)),
+                    ('PV log-base', lambda: sweep.matmul_err_A_log_base(pctx, Bq, qc, 4)),
+                    ('PV B-sweep', lambda: sweep.matmul_err_B(pctx, _logq(), cs, cz, 4, True))):
+        fn()
+        torch.cuda.synchronize()
+        ops.profile_reset(True)
+        t = timed(fn, 2)
+        flops, ms, n = ops.profile_gemm_summary()
+        ops.profile_reset(False)
+        print(f'{tag}: {t:.2f} ms per sweep; GEMM kernel {ms / 3:.2f} ms in {n // 3} launches '
+              f'({flops / ms / 1e9:.0f} TFLOP/s); generator+rest {t - ms / 3:.2f} ms')
+
+
+def _logq():
+    from adalog_b200.quantizers import AdaLogQuantizer
+    a = AdaLogQuantizer(3).to(DEV)
+    a.scale = torch.nn.Parameter(torch.ones(1, 1, 1, 1, device=DEV))
+    a.inited = True
+    return a
+
+
 if __name__ == '__main__':
     print(torch.cuda.get_device_name(0))
     good = probe_tile()
     print('TILE', 'OK' if good else 'BROKEN')
     if good and len(sys.argv) > 1 and sys.argv[1] == 'perf':
         perf_probe()
+    if good and len(sys.argv) > 1 and sys.argv[1] == 'matmul':
+        perf_matmul()
