@@ -20,7 +20,7 @@ class GemmErrArgs(ctypes.Structure):
     _fields_ = [
         ('A', c_vp), ('Bm', c_vp), ('a_rows', c_i64), ('b_rows', c_i64),
         ('KB', ctypes.c_int32), ('N', ctypes.c_int32), ('BN', ctypes.c_int32), ('U', ctypes.c_int32),
-        ('UG', ctypes.c_int32), ('upc', ctypes.c_int32), ('S', ctypes.c_int32),
+        ('UG', ctypes.c_int32), ('upc', ctypes.c_int32), ('S', ctypes.c_int32), ('dtype', ctypes.c_int32),
         ('brpg', c_i64), ('g_base', c_i64), ('u_base', c_i64),
         ('y', c_vp), ('ldy', c_i64),
         ('rs', c_vp), ('rb', c_vp), ('rs_div', c_i64), ('rs_mod', c_i64),
@@ -37,15 +37,15 @@ SIGNATURES = {
     'adalog_twin_fakequant_f32': [c_vp, c_vp, c_i64, c_vp, c_int, c_vp],
     'adalog_sweep_err_w_self': [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     'adalog_sweep_err_a_self': [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
-    'adalog_gen_uniform_fixed': [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_vp],
+    'adalog_gen_uniform_fixed': [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp],
     'adalog_gen_uniform_cand': [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
-                                c_vp, c_int, c_int, c_vp, c_vp],
+                                c_vp, c_int, c_int, c_vp, c_int, c_vp],
     'adalog_gen_log_cand': [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp],
     'adalog_gen_log_fixed': [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp],
     'adalog_gen_split3': [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_vp],
     'adalog_cand_gemm_err_grid': [ctypes.POINTER(GemmErrArgs)],
     'adalog_cand_gemm_err': [ctypes.POINTER(GemmErrArgs), c_vp],
-    'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+    'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
 }
 
 _lib = None

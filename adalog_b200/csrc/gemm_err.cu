@@ -109,6 +109,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
+// kind::i8: D=S32 (2 @ bit4), A = B = signed int8 (1 @ bit7, 1 @ bit10), no saturation, K-major both
+__device__ __forceinline__ uint32_t make_idesc_i8(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -149,7 +161,7 @@ struct KArgs {
 // MODE_PLAIN: yhat = rs*D (attention matmuls)
 enum { MODE_CS = 0, MODE_RB = 1, MODE_PLAIN = 2 };
 
-template <int MODE, bool DEBUG>
+template <int MODE, bool DEBUG, bool I8>
 __global__ void __launch_bounds__(kThreads, 1)
 cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -203,8 +215,9 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < a.KB; ++kb) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
           mbar_expect_tx(&tail->full[stage], tx);
-          tma_load_2d(&tmA, &tail->full[stage], sA + (size_t)stage * kABytes, kb * kBK, u * kBM);
-          tma_load_2d(&tmB, &tail->full[stage], sB + (size_t)stage * kBBytes, kb * kBK, (int)brow);
+          const int kel = kb * (I8 ? 2 * kBK : kBK);    // K coordinate in elements (64 bf16 or 128 int8 = 128 bytes)
+          tma_load_2d(&tmA, &tail->full[stage], sA + (size_t)stage * kABytes, kel, u * kBM);
+          tma_load_2d(&tmB, &tail->full[stage], sB + (size_t)stage * kBBytes, kel, (int)brow);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -213,7 +226,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t idesc = make_idesc(a.BN);
+      const uint32_t idesc = I8 ? make_idesc_i8(a.BN) : make_idesc(a.BN);
       for (int t = 0; t < n_tiles; ++t) {
         const uint32_t as = t & 1, aphase = (t >> 1) & 1;
         mbar_wait(&tail->tempty[as], aphase ^ 1);
@@ -225,8 +238,10 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)stage * kABytes));
           const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * kBBytes));
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) { // UMMA_K = 16 bf16 or 32 int8 = 32 bytes -> +2 in the (addr>>4) field
+            if (I8) umma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&tail->empty[stage]);    // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -261,6 +276,8 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // four independent accumulators (same instruction sequence for every lane = candidate, so equal candidates still
     // produce bit-equal sums)
     float acc4[4];
+    // accumulator word -> FP32: kind::f16 accumulates in FP32, kind::i8 in S32 (exact integer dot products)
+    auto accf = [](uint32_t w) -> float { return I8 ? __int2float_rn((int)w) : __uint_as_float(w); };
     auto quad = [&](const uint32_t (&d)[32], int j, int c0, int buf, float rs, float rb) {
       const float4 yv = *reinterpret_cast<const float4*>(&tail_s.ysm[buf][c0 + j]);
       const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
@@ -269,19 +286,19 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float diff = fmaf(-rs, __uint_as_float(d[j + e]) * c4[e], y4[e]);
+          const float diff = fmaf(-rs, accf(d[j + e]) * c4[e], y4[e]);
           acc4[e] = fmaf(diff, diff, acc4[e]);
         }
       } else if (MODE == MODE_RB) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float diff = y4[e] - fmaf(rs, __uint_as_float(d[j + e]), rb);
+          const float diff = y4[e] - fmaf(rs, accf(d[j + e]), rb);
           acc4[e] = fmaf(diff, diff, acc4[e]);
         }
       } else {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float diff = fmaf(-rs, __uint_as_float(d[j + e]), y4[e]);
+          const float diff = fmaf(-rs, accf(d[j + e]), y4[e]);
           acc4[e] = fmaf(diff, diff, acc4[e]);
         }
       }
@@ -291,7 +308,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (DEBUG) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = __uint_as_float(d[j]);
+          if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = accf(d[j]);
       }
       if (lim == 32) {
 #pragma unroll
@@ -305,7 +322,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (j >= lim4 && j < lim) {
-            float dv = __uint_as_float(d[j]);
+            float dv = accf(d[j]);
             if (HAS_CS) dv *= tail_s.csm[buf][c0 + j];
             const float diff = tail_s.ysm[buf][c0 + j] - fmaf(rs, dv, rb);
             acc4[j & 3] = fmaf(diff, diff, acc4[j & 3]);
@@ -395,16 +412,17 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box [box_rows, 64], 128-byte swizzle
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+// 2-D row-major [rows, cols] operand (bf16 or int8), box [box_rows, 128 bytes], 128-byte swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows, bool i8) {
   auto enc = get_encode();
   if (!enc) return fail(-20, "cuTensorMapEncodeTiled entry point not found");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(-21, "operand base not 16-byte aligned");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * (i8 ? 1 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(i8 ? 2 * kBK : kBK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                   dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-22, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r,
@@ -417,6 +435,7 @@ static int validate(const adalog_gemm_err_args* a, bool need_partial) {
   ADALOG_REQUIRE(a->KB > 0 && a->N > 0 && a->U > 0 && a->UG > 0 && a->upc > 0 && a->S > 0, -1,
                  "cand_gemm_err: non-positive size");
   ADALOG_REQUIRE(a->BN >= 16 && a->BN <= kMaxBN && a->BN % 16 == 0, -1, "cand_gemm_err: BN must be a multiple of 16 in [16,256]");
+  ADALOG_REQUIRE(a->dtype == ADALOG_BF16 || a->dtype == ADALOG_I8, -1, "cand_gemm_err: dtype must be ADALOG_BF16 or ADALOG_I8");
   ADALOG_REQUIRE(a->U % a->UG == 0, -1, "cand_gemm_err: U must be a multiple of UG");
   ADALOG_REQUIRE(a->a_rows >= (int64_t)a->U * kBM, -1, "cand_gemm_err: A has fewer than U*128 rows");
   ADALOG_REQUIRE(a->rs_div > 0 && a->rs_mod > 0 && a->rs, -1, "cand_gemm_err: row scale required");
@@ -435,21 +454,30 @@ static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st) {
   k.y = a->y; k.ldy = a->ldy; k.rs = a->rs; k.rb = a->rb; k.rs_div = a->rs_div; k.rs_mod = a->rs_mod;
   k.cs = a->cs; k.cb = a->cb; k.partial = a->partial; k.dbg = dbg;
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, a->A, a->a_rows, (int64_t)a->KB * kBK, kBM);
+  const bool i8 = a->dtype == ADALOG_I8;
+  const int64_t cols = (int64_t)a->KB * (i8 ? 2 * kBK : kBK);
+  int rc = make_map(&tmA, a->A, a->a_rows, cols, kBM, i8);
   if (rc) return rc;
-  rc = make_map(&tmB, a->Bm, a->b_rows, (int64_t)a->KB * kBK, a->BN);
+  rc = make_map(&tmB, a->Bm, a->b_rows, cols, a->BN, i8);
   if (rc) return rc;
   dim3 grid((unsigned)((a->U / a->UG) * k.cpg), (unsigned)a->S);
-#define ADALOG_LAUNCH_GEMM(MD, DBG)                                                                           \
+#define ADALOG_LAUNCH_GEMM(MD, DBG, I8)                                                                       \
   do {                                                                                                        \
-    cudaFuncSetAttribute(cand_gemm_err_kernel<MD, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+    cudaFuncSetAttribute(cand_gemm_err_kernel<MD, DBG, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                          (int)kSmemBytes);                                                                    \
-    cand_gemm_err_kernel<MD, DBG><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);                           \
+    cand_gemm_err_kernel<MD, DBG, I8><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);                       \
   } while (0)
-  if (dbg)         ADALOG_LAUNCH_GEMM(MODE_PLAIN, true);
-  else if (a->cs)  ADALOG_LAUNCH_GEMM(MODE_CS, false);
-  else if (a->rb)  ADALOG_LAUNCH_GEMM(MODE_RB, false);
-  else             ADALOG_LAUNCH_GEMM(MODE_PLAIN, false);
+  if (i8) {
+    if (dbg)         ADALOG_LAUNCH_GEMM(MODE_PLAIN, true, true);
+    else if (a->cs)  ADALOG_LAUNCH_GEMM(MODE_CS, false, true);
+    else if (a->rb)  ADALOG_LAUNCH_GEMM(MODE_RB, false, true);
+    else             ADALOG_LAUNCH_GEMM(MODE_PLAIN, false, true);
+  } else {
+    if (dbg)         ADALOG_LAUNCH_GEMM(MODE_PLAIN, true, false);
+    else if (a->cs)  ADALOG_LAUNCH_GEMM(MODE_CS, false, false);
+    else if (a->rb)  ADALOG_LAUNCH_GEMM(MODE_RB, false, false);
+    else             ADALOG_LAUNCH_GEMM(MODE_PLAIN, false, false);
+  }
 #undef ADALOG_LAUNCH_GEMM
   return check_launch("cand_gemm_err");
 }
@@ -472,7 +500,7 @@ int adalog_cand_gemm_err(const adalog_gemm_err_args* a, void* stream) {
   return launch(a, nullptr, (cudaStream_t)stream);
 }
 
-int adalog_debug_gemm_tile(const uint16_t* A, const uint16_t* Bm, int KB, int N, float* D, void* stream) {
+int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, int dtype, void* stream) {
   ADALOG_REQUIRE(A && Bm && D && KB > 0 && N > 0, -1, "debug_gemm_tile: bad arguments");
   // y = 0, rs = 1: scratch taken from D's tail is not available, so use small static device buffers
   static float* zeros = nullptr;
@@ -490,7 +518,7 @@ int adalog_debug_gemm_tile(const uint16_t* A, const uint16_t* Bm, int KB, int N,
   ADALOG_REQUIRE(N <= 65536, -1, "debug_gemm_tile: N too large");
   adalog_gemm_err_args a;
   memset(&a, 0, sizeof(a));
-  a.A = A; a.Bm = Bm; a.a_rows = kBM; a.b_rows = N; a.KB = KB; a.N = N;
+  a.A = A; a.Bm = Bm; a.a_rows = kBM; a.b_rows = N; a.KB = KB; a.N = N; a.dtype = dtype;
   a.BN = N >= kMaxBN ? kMaxBN : ((N + 15) / 16) * 16;
   a.U = 1; a.UG = 1; a.upc = 1; a.S = 1; a.brpg = N; a.g_base = 0; a.u_base = 0;
   a.y = zeros; a.ldy = 0; a.rs = ones; a.rb = nullptr; a.rs_div = 1; a.rs_mod = 1; a.cs = nullptr; a.cb = nullptr;

@@ -275,6 +275,13 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 // operand generators (bf16 integer parts; K-major rows of pitch kpad, zero padded)
 // ------------------------------------------------------------------------------------------------
+// four small-integer floats -> four int8 (two's complement) in one word: the low mantissa byte of v + 1.5*2^23
+__device__ __forceinline__ uint32_t pack_i8x4(float a, float b, float c, float d) {
+  const uint32_t ua = __float_as_uint(__fadd_rn(a, 12582912.0f)), ub = __float_as_uint(__fadd_rn(b, 12582912.0f));
+  const uint32_t uc = __float_as_uint(__fadd_rn(c, 12582912.0f)), ud = __float_as_uint(__fadd_rn(d, 12582912.0f));
+  return __byte_perm(__byte_perm(ua, ub, 0x0040), __byte_perm(uc, ud, 0x0040), 0x5410);
+}
+
 __device__ __forceinline__ void store8(uint16_t* dst, const float (&v)[8]) {
   uint4 o;
   o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -282,40 +289,55 @@ __device__ __forceinline__ void store8(uint16_t* dst, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(dst) = o;
 }
 
+template <bool I8>
 __global__ void __launch_bounds__(256) gen_uniform_fixed_kernel(const float* __restrict__ x, int64_t R, int K,
                                                                int64_t ldx, const float* __restrict__ scale,
                                                                const float* __restrict__ zp, int64_t g_div,
-                                                               int64_t g_mod, int nl, uint16_t* __restrict__ out,
+                                                               int64_t g_mod, int nl, void* __restrict__ out,
                                                                int kpad, float* __restrict__ rowsum) {
-  const int cpr = kpad >> 3;
+  constexpr int EPT = I8 ? 16 : 8;         // elements per 16-byte store
+  const int cpr = kpad / EPT;
   const int64_t total = R * cpr;
   const float L = (float)(2 * nl - 1);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / cpr;
-    const int kc = (int)(idx - r * cpr) << 3;
+    const int kc = (int)(idx - r * cpr) * EPT;
     const int64_t g = (r / g_div) % g_mod;
     const float s = __ldg(scale + g), z = __ldg(zp + g);
-    float v[8];
+    float v[EPT];
     float sum = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < EPT; ++j) {
       const int k = kc + j;
       v[j] = (k < K) ? uq_int(__ldg(x + r * ldx + k), s, z, L) : 0.0f;
       sum += v[j];
     }
-    store8(out + r * kpad + kc, v);
+    uint4 o;
+    if (I8) {
+      o.x = pack_i8x4(v[0], v[1], v[2], v[3]);   o.y = pack_i8x4(v[4], v[5], v[6], v[7]);
+      o.z = pack_i8x4(v[8 % EPT], v[9 % EPT], v[10 % EPT], v[11 % EPT]);
+      o.w = pack_i8x4(v[12 % EPT], v[13 % EPT], v[14 % EPT], v[15 % EPT]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + r * kpad + kc) = o;
+    } else {
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + r * kpad + kc) = o;
+    }
     if (rowsum && kc < K) atomicAdd(rowsum + r, sum);  // integers: exact, order independent
   }
 }
 
-template <int KREP, bool ROWSUM>
+template <int KREP, bool ROWSUM, bool I8>
 __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __restrict__ x, int K, int64_t ldx,
                                                               const float* __restrict__ cs,
                                                               const float* __restrict__ cz, int P, int64_t pstride,
                                                               int64_t gstride, int64_t g_div, int64_t g_mod,
-                                                              int64_t u_base, int nl, uint16_t* __restrict__ out,
+                                                              int64_t u_base, int nl, void* __restrict__ out_v,
                                                               int kpad, float* __restrict__ rowsum, int tpc) {
+  constexpr int EPT = I8 ? 16 : 8;         // elements per thread chunk = one 16-byte store
+  constexpr int ESZ = I8 ? 1 : 2;
+  uint8_t* out = reinterpret_cast<uint8_t*>(out_v);
   __shared__ float4 cand[ADALOG_P];
   __shared__ float rsum[ADALOG_P];
   const int64_t u = blockIdx.x;
@@ -331,46 +353,52 @@ __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __re
     rsum[p] = 0.0f;
   }
   __syncthreads();
-  const int cpr = kpad >> 3;
+  const int cpr = kpad / EPT;
   const int npg = blockDim.x / tpc;                      // host guarantees blockDim.x == tpc * npg
   const int lane_chunk = threadIdx.x % tpc, pg = threadIdx.x / tpc;
   const int per = ADALOG_P / gridDim.y;                  // candidates of this CTA: [p_lo, p_lo + per)
   const int p_lo = blockIdx.y * per;
-  const int64_t pitch = (int64_t)KREP * kpad;
+  const int64_t pitch = (int64_t)KREP * kpad * ESZ;      // bytes
   const int64_t dstep = (int64_t)npg * pitch;
   const int iters = (per - pg + npg - 1) / npg;
   const float* xrow = x + u * ldx;
   for (int ch = lane_chunk; ch < cpr; ch += tpc) {
-    const int kc = ch << 3;
-    const bool tail = kc + 8 > K;
-    float xv[8];
+    const int kc = ch * EPT;
+    const bool tail = kc + EPT > K;
+    float xv[EPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] = (kc + j < K) ? __ldg(xrow + kc + j) : 0.0f;
-    uint16_t* dst = out + (u * ADALOG_P + p_lo + pg) * pitch + kc;
+    for (int j = 0; j < EPT; ++j) xv[j] = (kc + j < K) ? __ldg(xrow + kc + j) : 0.0f;
+    uint8_t* dst = out + (u * ADALOG_P + p_lo + pg) * pitch + (int64_t)kc * ESZ;
     const float4* cp = cand + p_lo + pg;
     for (int it = 0; it < iters; ++it, dst += dstep, cp += npg) {
       const float4 c = *cp;
-      float v[8];
+      float v[EPT];
       bool unsafe = false;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = uq_int_fast(xv[j], c, unsafe);
-      if (unsafe) {                                      // ~3% of warps: redo the chunk on the IEEE path
+      for (int j = 0; j < EPT; ++j) v[j] = uq_int_fast(xv[j], c, unsafe);
+      if (unsafe) {                                      // a few % of warps: redo the chunk on the IEEE path
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = uq_int(xv[j], c.w, -c.y, c.z - c.y);
+        for (int j = 0; j < EPT; ++j) v[j] = uq_int(xv[j], c.w, -c.y, c.z - c.y);
       }
       if (tail) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (kc + j >= K) v[j] = 0.0f;
+        for (int j = 0; j < EPT; ++j) if (kc + j >= K) v[j] = 0.0f;
       }
       uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      if (I8) {
+        o.x = pack_i8x4(v[0], v[1], v[2], v[3]);   o.y = pack_i8x4(v[4], v[5], v[6], v[7]);
+        o.z = pack_i8x4(v[8 % EPT], v[9 % EPT], v[10 % EPT], v[11 % EPT]);
+        o.w = pack_i8x4(v[12 % EPT], v[13 % EPT], v[14 % EPT], v[15 % EPT]);
+      } else {
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      }
 #pragma unroll
-      for (int rep = 0; rep < KREP; ++rep) *reinterpret_cast<uint4*>(dst + (int64_t)rep * kpad) = o;
+      for (int rep = 0; rep < KREP; ++rep) *reinterpret_cast<uint4*>(dst + (int64_t)rep * kpad * ESZ) = o;
       if (ROWSUM) {
         float sum = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[j];
+        for (int j = 0; j < EPT; ++j) sum += v[j];
         atomicAdd(rsum + p_lo + pg + it * npg, sum);
       }
     }
@@ -680,33 +708,43 @@ int adalog_sweep_err_a_self(const float* x, int64_t n_total, int C, int per_chan
 }
 
 int adalog_gen_uniform_fixed(const float* x, int64_t R, int K, int64_t ldx, const float* scale, const float* zp,
-                             int64_t g_div, int64_t g_mod, int n_levels, uint16_t* out, int kpad, float* rowsum,
-                             void* stream) {
-  ADALOG_REQUIRE(x && scale && zp && out && R > 0 && K > 0 && kpad % ADALOG_BK == 0 && kpad >= K && g_div > 0 &&
-                     g_mod > 0, -1, "gen_uniform_fixed: bad arguments");
+                             int64_t g_div, int64_t g_mod, int n_levels, void* out, int kpad, float* rowsum,
+                             int dtype, void* stream) {
+  const int kb = dtype == ADALOG_I8 ? 128 : ADALOG_BK;
+  ADALOG_REQUIRE(x && scale && zp && out && R > 0 && K > 0 && kpad % kb == 0 && kpad >= K && g_div > 0 && g_mod > 0 &&
+                     (dtype == ADALOG_BF16 || dtype == ADALOG_I8), -1, "gen_uniform_fixed: bad arguments");
+  ADALOG_REQUIRE(dtype != ADALOG_I8 || n_levels <= 64, -2, "gen_uniform_fixed: int8 operands need n_bits <= 7");
   cudaStream_t st = (cudaStream_t)stream;
   if (rowsum) cudaMemsetAsync(rowsum, 0, (size_t)R * sizeof(float), st);
-  gen_uniform_fixed_kernel<<<grid_for(R * (kpad / 8), 256), 256, 0, st>>>(x, R, K, ldx, scale, zp, g_div, g_mod,
-                                                                         n_levels, out, kpad, rowsum);
+  if (dtype == ADALOG_I8)
+    gen_uniform_fixed_kernel<true><<<grid_for(R * (kpad / 16), 256), 256, 0, st>>>(x, R, K, ldx, scale, zp, g_div, g_mod,
+                                                                                  n_levels, out, kpad, rowsum);
+  else
+    gen_uniform_fixed_kernel<false><<<grid_for(R * (kpad / 8), 256), 256, 0, st>>>(x, R, K, ldx, scale, zp, g_div, g_mod,
+                                                                                  n_levels, out, kpad, rowsum);
   return check_launch("gen_uniform_fixed");
 }
 
 int adalog_gen_uniform_cand(const float* x, int64_t U, int K, int64_t ldx, const float* cs, const float* cz, int P,
                             int64_t pstride, int64_t gstride, int64_t g_div, int64_t g_mod, int64_t u_base,
-                            int n_levels, uint16_t* out, int kpad, int krep, float* rowsum, void* stream) {
-  ADALOG_REQUIRE(x && cs && cz && out && U > 0 && U < (1ll << 31) && K > 0 && kpad % ADALOG_BK == 0 && kpad >= K &&
-                     P > 0 && P <= ADALOG_P && (krep == 1 || krep == 3) && g_div > 0 && g_mod > 0, -1,
-                 "gen_uniform_cand: bad arguments");
-  const int cpr = kpad / 8;
-  const int tpc = cpr < 256 ? cpr : 256;                 // threads along K (8 elements each)
+                            int n_levels, void* out, int kpad, int krep, float* rowsum, int dtype, void* stream) {
+  const int kb = dtype == ADALOG_I8 ? 128 : ADALOG_BK;
+  ADALOG_REQUIRE(x && cs && cz && out && U > 0 && U < (1ll << 31) && K > 0 && kpad % kb == 0 && kpad >= K && P > 0 &&
+                     P <= ADALOG_P && (krep == 1 || krep == 3) && g_div > 0 && g_mod > 0 &&
+                     (dtype == ADALOG_BF16 || dtype == ADALOG_I8), -1, "gen_uniform_cand: bad arguments");
+  ADALOG_REQUIRE(dtype != ADALOG_I8 || (n_levels <= 64 && krep == 1 && !rowsum), -2,
+                 "gen_uniform_cand: int8 operands need n_bits <= 7, krep == 1 and no rowsum");
+  const int cpr = kpad / (dtype == ADALOG_I8 ? 16 : 8);
+  const int tpc = cpr < 256 ? cpr : 256;                 // threads along K (one 16-byte store each)
   const int npg = 256 / tpc;                             // candidate groups per CTA
   dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
   cudaStream_t st = (cudaStream_t)stream;
-#define ADALOG_LAUNCH_UCAND(KR, RS)                                                                                  \
-  gen_uniform_cand_kernel<KR, RS><<<grid, tpc * npg, 0, st>>>(x, K, ldx, cs, cz, P, pstride, gstride, g_div, g_mod,  \
-                                                               u_base, n_levels, out, kpad, rowsum, tpc)
-  if (krep == 1) { if (rowsum) ADALOG_LAUNCH_UCAND(1, true); else ADALOG_LAUNCH_UCAND(1, false); }
-  else           { if (rowsum) ADALOG_LAUNCH_UCAND(3, true); else ADALOG_LAUNCH_UCAND(3, false); }
+#define ADALOG_LAUNCH_UCAND(KR, RS, I8)                                                                              \
+  gen_uniform_cand_kernel<KR, RS, I8><<<grid, tpc * npg, 0, st>>>(x, K, ldx, cs, cz, P, pstride, gstride, g_div,     \
+                                                                   g_mod, u_base, n_levels, out, kpad, rowsum, tpc)
+  if (dtype == ADALOG_I8) ADALOG_LAUNCH_UCAND(1, false, true);
+  else if (krep == 1) { if (rowsum) ADALOG_LAUNCH_UCAND(1, true, false); else ADALOG_LAUNCH_UCAND(1, false, false); }
+  else                { if (rowsum) ADALOG_LAUNCH_UCAND(3, true, false); else ADALOG_LAUNCH_UCAND(3, false, false); }
 #undef ADALOG_LAUNCH_UCAND
   return check_launch("gen_uniform_cand");
 }

@@ -51,8 +51,13 @@ def _f32(t):
     return t.contiguous()
 
 
-def kpad(K):
-    return ((K + BK - 1) // BK) * BK
+BF16, I8 = 0, 1   # ADALOG_BF16 / ADALOG_I8
+
+
+def kpad(K, i8=False):
+    """operand row pitch in ELEMENTS: whole 128-byte swizzle rows (64 bf16 or 128 int8)"""
+    blk = 2 * BK if i8 else BK
+    return ((K + blk - 1) // blk) * blk
 
 
 def _prod(xs):
@@ -169,24 +174,27 @@ def _rows2d(x):
     return x
 
 
-def gen_uniform_fixed(x2d, scale_g, zp_g, g_div, g_mod, n_levels, want_rowsum=False):
+def gen_uniform_fixed(x2d, scale_g, zp_g, g_div, g_mod, n_levels, want_rowsum=False, i8=False):
     _cuda(x2d, scale_g, zp_g)
     x2d = _rows2d(_f32(x2d))
     R, K = x2d.shape
-    kp = kpad(K)
-    out = torch.empty(R, kp, dtype=torch.bfloat16, device=x2d.device)
+    kp = kpad(K, i8)
+    out = torch.empty(R, kp, dtype=torch.int8 if i8 else torch.bfloat16, device=x2d.device)
     rowsum = torch.empty(R, dtype=torch.float32, device=x2d.device) if want_rowsum else None
     call('adalog_gen_uniform_fixed', _p(x2d), R, K, x2d.stride(0), _p(_f32(scale_g).reshape(-1)),
-         _p(_f32(zp_g).reshape(-1)), int(g_div), int(g_mod), int(n_levels), _p(out), kp, _p(rowsum), _stream())
+         _p(_f32(zp_g).reshape(-1)), int(g_div), int(g_mod), int(n_levels), _p(out), kp, _p(rowsum),
+         I8 if i8 else BF16, _stream())
     return out, rowsum
 
 
-def gen_uniform_cand(x2d, u0, nu, cs, cz, P, pstride, gstride, g_div, g_mod, n_levels, out, krep=1, rowsum=None):
-    """rows [u0, u0+nu) of x2d -> out[(u*128+p), krep*kpad]."""
+def gen_uniform_cand(x2d, u0, nu, cs, cz, P, pstride, gstride, g_div, g_mod, n_levels, out, krep=1, rowsum=None,
+                     i8=False):
+    """rows [u0, u0+nu) of x2d -> out[(u*128+p), krep*kpad]  (bf16, or int8 when i8)."""
     K = x2d.shape[1]
     xs = x2d[u0:u0 + nu]
     call('adalog_gen_uniform_cand', _p(xs), nu, K, x2d.stride(0), _p(cs), _p(cz), int(P), int(pstride), int(gstride),
-         int(g_div), int(g_mod), int(u0), int(n_levels), _p(out), kpad(K), int(krep), _p(rowsum), _stream())
+         int(g_div), int(g_mod), int(u0), int(n_levels), _p(out), kpad(K, i8), int(krep), _p(rowsum),
+         I8 if i8 else BF16, _stream())
 
 
 def gen_log_cand(x2d, u0, nu, cs, cq, P, shift, mtab, n_levels, out):
@@ -226,13 +234,15 @@ def pick_bn(N):
 
 
 def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, ldy, rs, rb, rs_div, rs_mod, cs, cb,
-                  upc, S, BN=None, k_true=None):
-    """One launch of adalog_cand_gemm_err.  Returns FP64 partial [S, gridX, 128]."""
+                  upc, S, BN=None, k_true=None, i8=False):
+    """One launch of adalog_cand_gemm_err.  Returns FP64 partial [S, gridX, 128].  ka: operand pitch in elements."""
     BN = BN or pick_bn(N)
     a = GemmErrArgs()
     a.A, a.Bm = A.data_ptr(), Bm.data_ptr()
     a.a_rows, a.b_rows = int(a_rows), int(Bm.shape[0])
-    a.KB, a.N, a.BN, a.U, a.UG, a.upc, a.S = ka // BK, int(N), int(BN), int(U), int(UG), int(upc), int(S)
+    a.KB = ka // (2 * BK if i8 else BK)
+    a.dtype = I8 if i8 else BF16
+    a.N, a.BN, a.U, a.UG, a.upc, a.S = int(N), int(BN), int(U), int(UG), int(upc), int(S)
     a.brpg, a.g_base, a.u_base = int(brpg), int(g_base), int(u_base)
     a.y, a.ldy = y.data_ptr() + 4 * int(y_off), int(ldy)
     a.rs, a.rb = rs.data_ptr(), (rb.data_ptr() if rb is not None else None)
@@ -253,13 +263,15 @@ def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, l
 
 
 def debug_gemm_tile(A, Bm):
-    """D[128, N] = A[128, ka] @ Bm[N, ka]^T through the tcgen05 pipeline (test hook)."""
+    """D[128, N] = A[128, ka] @ Bm[N, ka]^T through the tcgen05 pipeline (test hook); bf16 or int8 operands."""
     _cuda(A, Bm)
-    assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16 and A.shape[0] == 128
+    assert A.dtype == Bm.dtype and A.dtype in (torch.bfloat16, torch.int8) and A.shape[0] == 128
+    i8 = A.dtype == torch.int8
     ka = A.shape[1]
     N = Bm.shape[0]
     D = torch.zeros(128, N, dtype=torch.float32, device=A.device)
-    call('adalog_debug_gemm_tile', _p(A.contiguous()), _p(Bm.contiguous()), ka // BK, N, _p(D), _stream())
+    call('adalog_debug_gemm_tile', _p(A.contiguous()), _p(Bm.contiguous()), ka // (2 * BK if i8 else BK), N, _p(D),
+         I8 if i8 else BF16, _stream())
     return D
 
 

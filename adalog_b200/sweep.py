@@ -20,15 +20,18 @@ from .utils import dist as adist
 WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '768')) << 20
 NUM_SMS = 148
 R_BASE = 37.0
+# uniform x uniform sweeps (every quantizer up to 7 bits: |code - zp| <= 127) run on the INT8 tensor cores
+# (tcgen05.mma.kind::i8, S32 accumulation: exact) at twice the bf16 MMA rate and half the operand bytes
+USE_I8 = os.environ.get('ADALOG_B200_I8', '1') == '1'
 
 _workspaces = {}
 
 
-def _workspace(device, n_elems):
+def _workspace(device, n_bytes):
     key = (device.type, device.index)
     buf = _workspaces.get(key)
-    if buf is None or buf.numel() < n_elems:
-        buf = torch.empty(n_elems, dtype=torch.bfloat16, device=device)
+    if buf is None or buf.numel() < n_bytes:
+        buf = torch.empty(n_bytes, dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
 
@@ -74,7 +77,7 @@ def _launch_plan(nu, ug, NT):
 
 
 def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=1, rs_mod=1, cs=None, cb=None,
-                  k_true=None):
+                  k_true=None, i8=False):
     """Chunk the units through the bf16 workspace: generate candidate rows, launch the fused GEMM.
 
     gen_cand(u0, nu, out) fills out[nu*128, ka] for units [u0, u0+nu).
@@ -86,8 +89,8 @@ def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=
     """
     dev = Bm.device
     single = UG == U
-    unit_elems = ops.P_TILE * ka
-    max_units = max(1, (WS_BYTES // 2) // (unit_elems * 2))
+    unit_elems = ops.P_TILE * ka * (1 if i8 else 2)      # bytes of one unit's 128 candidate rows
+    max_units = max(1, (WS_BYTES // 2) // unit_elems)
     step = min(U, max_units) if single else min(U, max(1, max_units // UG) * UG)
     n_chunks = (U + step - 1) // step
     BN = ops.pick_bn(N)
@@ -100,7 +103,7 @@ def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=
         ug = nu if single else UG
         groups, upc, cpg, S = _launch_plan(nu, ug, NT)
         part = ops.cand_gemm_err(buf, nu * ops.P_TILE, Bm, ka, N, nu, ug, brpg, 0 if single else u0 // UG, u0, y,
-                                 u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN, k_true)
+                                 u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN, k_true, i8)
         return part.view(S, groups, cpg, ops.P_TILE).sum(dim=(0, 2))
 
     outs = []
@@ -197,8 +200,12 @@ def linear_err_a_self(ctx, cs, cz, n_levels, channel_wise):
     return (-(esum / denom)).float()
 
 
-def _fixed_act_operand(ctx, aq):
-    """quant_input(x) as an exact bf16 operand + the epilogue factors it implies.
+def _i8_ok(*n_levels):
+    return USE_I8 and all(nl <= 64 for nl in n_levels)
+
+
+def _fixed_act_operand(ctx, aq, i8=False):
+    """quant_input(x) as an exact bf16 / int8 operand + the epilogue factors it implies.
 
     returns (Bm [tokens, ka], a_scale (python float tensor [1] FP64), shift or None)
     uniform:       x_hat = a_scale * I
@@ -210,7 +217,7 @@ def _fixed_act_operand(ctx, aq):
         Bm = ops.gen_log_fixed(ctx.x2d, aq.scale, aq.q, aq.shift, aq.table1, m2, nl)
         return Bm, _f32(aq.scale).double().reshape(1) / (4 * nl - 2), _f32(aq.shift).double().reshape(1)
     s, z = uniform_operand_params(aq)
-    Bm, _ = ops.gen_uniform_fixed(ctx.x2d, s, z, 1 << 62, 1, aq.n_levels)
+    Bm, _ = ops.gen_uniform_fixed(ctx.x2d, s, z, 1 << 62, 1, aq.n_levels, i8=i8)
     return Bm, s.double(), None
 
 
@@ -221,8 +228,9 @@ def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
     P = cs.shape[0]
     dev = weight3.device
     c2, z2 = _cand2d(cs, cz)                         # [P, out]
-    Bm, a_scale, shift = _fixed_act_operand(ctx, aq)
-    ka = ops.kpad(in_f)
+    i8 = not getattr(aq, 'is_log', False) and _i8_ok(aq.n_levels, n_levels_w)
+    Bm, a_scale, shift = _fixed_act_operand(ctx, aq, i8)
+    ka = ops.kpad(in_f, i8)
     W2d = _f32(weight3).reshape(out_f, in_f)
     c2p = _pad128(c2.t().contiguous())               # [out, 128] candidate scales per row
     rs = (c2p.double() * a_scale).float().contiguous()
@@ -232,7 +240,7 @@ def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
 
     def gen(u0, nu, out):
         ops.gen_uniform_cand(W2d, u0, nu, c2, z2, P, out_f, 1, 1, out_f, n_levels_w, out, 1,
-                             rowsum[u0:] if rowsum is not None else None)
+                             rowsum[u0:] if rowsum is not None else None, i8=i8)
         if shift is not None:
             # sum_k (v s - shift) w = s sum_k v w - shift sum_k w  (linear.py:879): fold the second term into the
             # row bias, using the integer row sums the generator just produced (same stream, ordered)
@@ -240,16 +248,16 @@ def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
                               - shift * c2p[u0:u0 + nu].double() * rowsum[u0:u0 + nu].double()).float()
 
     ntok = ctx.x2d.shape[0]
-    res = run_cand_gemm(gen, out_f, ka, 1, Bm, 0, ntok, ctx.yT, ntok, rs, rb, 1, out_f, k_true=in_f)
+    res = run_cand_gemm(gen, out_f, ka, 1, Bm, 0, ntok, ctx.yT, ntok, rs, rb, 1, out_f, k_true=in_f, i8=i8)
     res = adist.all_reduce_sum(res)                  # [out, 128]
     sims = -(res[:, :P] / ctx.tok_per_sample)
     return sims.t().float().reshape(P, n_V, rows)
 
 
-def _fixed_weight_operand(weight3, wq):
+def _fixed_weight_operand(weight3, wq, i8=False):
     n_V, rows, in_f = weight3.shape
     s, z = uniform_operand_params(wq)
-    Bm, colsum = ops.gen_uniform_fixed(_f32(weight3).reshape(-1, in_f), s, z, 1, n_V * rows, wq.n_levels, True)
+    Bm, colsum = ops.gen_uniform_fixed(_f32(weight3).reshape(-1, in_f), s, z, 1, n_V * rows, wq.n_levels, not i8, i8)
     return Bm, s, colsum
 
 
@@ -259,18 +267,19 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
     out_f = n_V * rows
     P = cs.shape[-1]
     dev = weight3.device
-    Bm, s_w, _ = _fixed_weight_operand(weight3, wq)
+    i8 = _i8_ok(wq.n_levels, n_levels_a)
+    Bm, s_w, _ = _fixed_weight_operand(weight3, wq, i8)
     c1, z1 = _f32(cs).reshape(-1), _f32(cz).reshape(-1)
-    ka = ops.kpad(in_f)
+    ka = ops.kpad(in_f, i8)
 
     def gen(u0, nu, out):
-        ops.gen_uniform_cand(ctx.x2d, u0, nu, c1, z1, P, 1, 0, 1 << 62, 1, n_levels_a, out)
+        ops.gen_uniform_cand(ctx.x2d, u0, nu, c1, z1, P, 1, 0, 1 << 62, 1, n_levels_a, out, i8=i8)
 
     rs = _pad128(c1).contiguous()
     cb = _f32(bias) if bias is not None else torch.zeros(out_f, device=dev)
     ntok = ctx.x2d.shape[0]
     res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
-                        k_true=in_f)
+                        k_true=in_f, i8=i8)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
     return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
 

@@ -29,7 +29,9 @@ extern "C" {
 #endif
 
 #define ADALOG_P 128          /* candidate rows of one unit tile */
-#define ADALOG_BK 64          /* bf16 elements per 128-byte swizzled K block */
+#define ADALOG_BK 64          /* bf16 elements per 128-byte swizzled K block (128 for int8 operands) */
+#define ADALOG_BF16 0         /* operand dtype: bf16 (any quantizer; exact for |int| <= 256 and m*2^-e) */
+#define ADALOG_I8 1           /* operand dtype: int8 (uniform quantizers up to 7 bits; tcgen05 kind::i8, S32 accumulate) */
 
 int adalog_version(void);
 const char* adalog_last_error(void);
@@ -69,22 +71,23 @@ int adalog_sweep_err_a_self(const float* x, int64_t n_total, int C, int per_chan
                             const float* cz, int P, int n_levels, double* partial, int nsplit, void* stream);
 
 /* ---------------------------------------------------------------- operand generators for the candidate GEMM
- * All generators read FP32 rows with unit K stride and write bf16 rows of pitch `kpad` (multiple of 64,
- * zero filled beyond K).  Values are the INTEGER part of the fake-quantised tensor (code - zp, or m*2^-e for
- * the log family) which bf16 holds exactly; scales are applied in the GEMM epilogue. */
+ * All generators read FP32 rows with unit K stride and write operand rows of pitch `kpad` ELEMENTS (a multiple of
+ * 64 for bf16, of 128 for int8, i.e. whole 128-byte swizzle rows; zero filled beyond K).  Values are the INTEGER
+ * part of the fake-quantised tensor (code - zp, or m*2^-e for the log family) which the operand type holds
+ * exactly; scales are applied in the GEMM epilogue.  `dtype` is ADALOG_BF16 or ADALOG_I8 (uniform only). */
 
 /* fixed operand, uniform quantizer (the non-searched side: linear.py:373 quant_input / :406 quant_weight_bias,
  * matmul.py:141,179).  group(r) = (r / g_div) % g_mod.  rowsum (optional) = sum_k value. */
 int adalog_gen_uniform_fixed(const float* x, int64_t R, int K, int64_t ldx, const float* scale, const float* zp,
-                             int64_t g_div, int64_t g_mod, int n_levels, uint16_t* out, int kpad, float* rowsum,
-                             void* stream);
+                             int64_t g_div, int64_t g_mod, int n_levels, void* out, int kpad, float* rowsum,
+                             int dtype, void* stream);
 
 /* candidate operand, uniform quantizer (linear.py:369-370, :409-410, matmul.py:150-151, :188-189, conv.py:237-238).
  * out row (u*128 + p); candidate p of unit u uses cs/cz[p*pstride + ((u_base+u)/g_div % g_mod)*gstride].
  * krep in {1,3}: the K block is repeated krep times along the row (pitch krep*kpad) to pair with a split-3 operand. */
 int adalog_gen_uniform_cand(const float* x, int64_t U, int K, int64_t ldx, const float* cs, const float* cz, int P,
                             int64_t pstride, int64_t gstride, int64_t g_div, int64_t g_mod, int64_t u_base,
-                            int n_levels, uint16_t* out, int kpad, int krep, float* rowsum, void* stream);
+                            int n_levels, void* out, int kpad, int krep, float* rowsum, int dtype, void* stream);
 
 /* candidate operand, AdaLog search form (linear.py:872-878, :913-919; matmul.py:337-342).
  * per candidate p: scale cs[p] (NULL: unscaled & unclamped, the post-softmax form) and base cq[p] (int64);
@@ -106,16 +109,16 @@ int adalog_gen_split3(const float* x, int64_t R, int K, int64_t ldx, uint16_t* o
  * replaces: the F.linear / @ / F.conv2d + _get_similarity + mean/sum chains of linear.py:355-384, :394-423,
  * :856-890, :898-931, matmul.py:135-163, :173-201, :321-351, conv.py:226-256.
  *
- * A  [U*128, ka] bf16  : candidate operand, one 128-row tile per unit (row = u*128 + p), ka = KB*64.
- * Bm [G*brpg, ka] bf16 : fixed operand, group g = (g_base + u/UG) owns rows [g*brpg, g*brpg + N).
- * D[p, n] = sum_k A[u*128+p, k] * Bm[g*brpg + n, k]        (tcgen05.mma, FP32 accumulate in TMEM)
+ * A  [U*128, ka] : candidate operand, one 128-row tile per unit (row = u*128 + p); ka = KB*64 (bf16) / KB*128 (int8).
+ * Bm [G*brpg, ka]: fixed operand, group g = (g_base + u/UG) owns rows [g*brpg, g*brpg + N).
+ * D[p, n] = sum_k A[u*128+p, k] * Bm[g*brpg + n, k]   (tcgen05.mma kind::f16 -> FP32, or kind::i8 -> S32, in TMEM)
  * yhat    = rs[ri+p] * (cs ? cs[n]*D : D) + (rb ? rb[ri+p] : 0),  ri = ((u_base+u)/rs_div % rs_mod)*128
  * e[p]   += (y[u*ldy + n] - (cb ? cb[n] : 0) - yhat)^2      summed over the CTA's units and N tiles
  * partial[(blockIdx.y*gridDim.x + blockIdx.x)*128 + p] = e[p] (FP64).  gridDim = (G_chunk * cpg, S):
  * CTA x handles units [g*UG + ci*upc, +upc) of group g = x / cpg, ci = x % cpg; CTA y handles N tiles
  * [y*NT/S, (y+1)*NT/S).  The partition is static, so equal candidates produce bit-equal sums. */
 typedef struct {
-  const uint16_t* A;  const uint16_t* Bm;
+  const void* A;      const void* Bm;
   int64_t a_rows;     int64_t b_rows;      /* allocated rows of A / Bm (TMA bounds) */
   int32_t KB;         /* K blocks of 64 */
   int32_t N;          /* valid columns per group */
@@ -124,6 +127,7 @@ typedef struct {
   int32_t UG;         /* units per group */
   int32_t upc;        /* units per CTA */
   int32_t S;          /* N-tile splits */
+  int32_t dtype;      /* ADALOG_BF16 | ADALOG_I8 */
   int64_t brpg;       /* Bm rows per group */
   int64_t g_base;     int64_t u_base;
   const float* y;     int64_t ldy;
@@ -138,7 +142,7 @@ int adalog_cand_gemm_err(const adalog_gemm_err_args* a, void* stream);
 
 /* plain (non-candidate) debug GEMM through the same tcgen05 pipeline: D[m,n] FP32 for A [128,ka], Bm [N,ka];
  * used by the tests to validate descriptors / swizzle / TMEM addressing in isolation. */
-int adalog_debug_gemm_tile(const uint16_t* A, const uint16_t* Bm, int KB, int N, float* D, void* stream);
+int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -181,6 +181,20 @@ def test_generators_exact():
     ref = (torch.round(x[:, None, :] / cs.t()[:, :, None]) + cz.t()[:, :, None]).clamp(0, 15) - cz.t()[:, :, None]
     assert torch.equal(buf.view(37, 128, 128)[:, :, :100].float(), ref)
     assert torch.equal(rs, ref.sum(-1))
+    # int8 operands (uniform quantizers up to 7 bits), pitch = 128-element blocks
+    for nl8 in (8, 64):
+        L = 2 * nl8 - 1
+        z8 = torch.randint(0, L + 1, (37,), device=DEV).float()
+        out8, _ = ops.gen_uniform_fixed(x, s, z8, 1, 37, nl8, i8=True)
+        ref8 = (torch.round(x / s[:, None]) + z8[:, None]).clamp(0, L) - z8[:, None]
+        assert out8.dtype == torch.int8 and out8.shape == (37, 128)
+        assert torch.equal(out8[:, :100].float(), ref8) and not out8[:, 100:].any()
+        cz8 = torch.randint(0, L + 1, (P, 37), device=DEV).float()
+        buf8 = torch.empty(37 * 128, 128, dtype=torch.int8, device=DEV)
+        ops.gen_uniform_cand(x, 0, 37, cs, cz8, P, 37, 1, 1, 37, nl8, buf8, i8=True)
+        ref8 = (torch.round(x[:, None, :] / cs.t()[:, :, None]) + cz8.t()[:, :, None]).clamp(0, L) - cz8.t()[:, :, None]
+        assert torch.equal(buf8.view(37, 128, 128)[:, :, :100].float(), ref8)
+        assert not buf8.view(37, 128, 128)[:, :, 100:].any()
     # split-3 carries FP32 exactly
     x3 = ops.gen_split3(x).float().view(37, 3, 128)
     assert torch.equal(x3.sum(1)[:, :100], x)

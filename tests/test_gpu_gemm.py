@@ -19,13 +19,16 @@ MATMUL = ['matmul_qk_a4', 'matmul_qk_a3', 'matmul_qk_a6_pooled', 'matmul_pv_s4a4
 CONV = ['conv_patch_w4', 'conv_patch_w6']
 
 
-@pytest.mark.parametrize('ka,N', [(64, 16), (64, 64), (128, 208), (256, 256), (768, 300), (192, 1000), (3072, 96)])
-def test_tcgen05_tile_exact(ka, N):
-    """integer-valued bf16 operands: the TMEM accumulator must equal the integer matmul exactly"""
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.int8])
+@pytest.mark.parametrize('ka,N', [(128, 16), (128, 64), (128, 208), (256, 256), (768, 300), (384, 1000), (3072, 96)])
+def test_tcgen05_tile_exact(ka, N, dtype):
+    """integer-valued bf16 (kind::f16 -> FP32) and int8 (kind::i8 -> S32) operands: the TMEM accumulator must equal
+    the integer matmul exactly"""
     from adalog_b200 import ops
     torch.manual_seed(ka + N)
-    A = torch.randint(-39, 40, (128, ka), device=DEV).to(torch.bfloat16)
-    B = torch.randint(-39, 40, (N, ka), device=DEV).to(torch.bfloat16)
+    hi = 40 if dtype == torch.bfloat16 else 128
+    A = torch.randint(-hi + 1, hi, (128, ka), device=DEV).to(dtype)
+    B = torch.randint(-hi + 1, hi, (N, ka), device=DEV).to(dtype)
     D = ops.debug_gemm_tile(A, B)
     ref = A.double() @ B.double().t()
     torch.cuda.synchronize()
