@@ -12,6 +12,7 @@
 #include "../../include/adalog_b200.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace adalog {
 
@@ -24,7 +25,8 @@ constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KiB
 constexpr uint32_t kBBytes = kMaxBN * kBK * 2;     // 32 KiB
 constexpr uint32_t kTmemCols = 512;
 constexpr int kEpiWarp0 = 4;            // warps 0-3: TMA producer, MMA issuer + TMEM allocator, two idle
-constexpr int kEpiWarps = 8;            // two epilogue warps per scheduler (TLP hides the FP32 dependent-issue latency)
+constexpr int kEpiWarps = 8;            // two epilogue warps per scheduler (16 was measured slower: register cap + barrier cost)
+constexpr int kEpiGroups = kEpiWarps / 4; // column groups: group g takes the 32-column slabs g, g+G, g+2G, ...
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 384
 
@@ -39,7 +41,7 @@ struct __align__(16) SmemTail {
   uint64_t tempty[kAccStages];
   uint32_t tmem_base;
   uint32_t pad;
-  double comb[kBM];           // second epilogue group's sums, folded into the first group's at the end
+  double comb[kEpiGroups - 1][kBM];   // sums of column groups 1.., folded into group 0's in fixed order at the end
 };
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * (kABytes + kBBytes);
 
@@ -159,7 +161,7 @@ struct KArgs {
 // ---------------------------------------------------------------- the kernel
 // MODE_CS: yhat = rs*(cs[n]*D), y' = y - cb[n] (linear A-side sweeps); MODE_RB: yhat = rs*D + rb (W-side sweeps);
 // MODE_PLAIN: yhat = rs*D (attention matmuls)
-enum { MODE_CS = 0, MODE_RB = 1, MODE_PLAIN = 2 };
+enum { MODE_CS = 0, MODE_RB = 1, MODE_PLAIN = 2, MODE_NOEPI = 3 /* diagnostic: pipeline only, no epilogue math */ };
 
 template <int MODE, bool DEBUG, bool I8>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -254,9 +256,9 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // slabs with index == eg (mod 2).  Every candidate therefore has two partial sums, folded in fixed order at the end.
     constexpr bool HAS_CS = MODE == MODE_CS;
     const int ew = warp - kEpiWarp0;
-    const int eg = ew >> 2;
+    const int eg = ew >> 2;                                 // column group 0..kEpiGroups-1
     const int et = ((ew & 3) << 5) | lane;                  // 0..127 = candidate p = TMEM lane
-    const int st = threadIdx.x - kEpiWarp0 * 32;            // 0..255: staging slot (one y column each)
+    const int st = threadIdx.x - kEpiWarp0 * 32;            // 0..kEpiThreads-1: staging slot (one y column each)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     double acc64 = 0.0;
     float rs = 0.0f, rb = 0.0f;
@@ -267,7 +269,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto prefetch = [&](int u, int n0) {
       const int n = n0 + st;
       float yv = 0.0f, bv = 0.0f, cv = 0.0f;
-      if (st < a.BN && n < a.N) {
+      if (st < kMaxBN && st < a.BN && n < a.N) {
         yv = __ldg(a.y + (long long)u * a.ldy + n);
         if (HAS_CS) { bv = __ldg(a.cb + n); cv = __ldg(a.cs + n); }
       }
@@ -310,7 +312,9 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int j = 0; j < 32; ++j)
           if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = accf(d[j]);
       }
-      if (lim == 32) {
+      if (MODE == MODE_NOEPI) {
+        acc4[0] += __uint_as_float(d[0]);
+      } else if (lim == 32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) quad(d, j, c0, buf, rs, rb);
       } else {
@@ -350,8 +354,10 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       const uint32_t as = t & 1, aphase = (t >> 1) & 1;
       const int buf = t & 1;
-      tail_s.ysm[buf][st] = yreg - breg;
-      if (HAS_CS) tail_s.csm[buf][st] = creg;
+      if (st < kMaxBN) {
+        tail_s.ysm[buf][st] = yreg - breg;
+        if (HAS_CS) tail_s.csm[buf][st] = creg;
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (t + 1 < n_tiles) prefetch(cu, (nt0 + cnt) * a.BN);
       if (ri_t != cur_ri) {
@@ -363,19 +369,20 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
       acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.0f;
       const uint32_t tbase = tmem_base + lane_base + as * kMaxBN;
-      // this group's slabs eg, eg+2, eg+4, ...; TMEM -> registers double buffered: the load of the next slab is in
+      // this group's slabs eg, eg+G, eg+2G, ...; TMEM -> registers double buffered: the load of the next slab is in
       // flight while the current one is reduced
       const int nslab = (ncols + 31) >> 5;
+      constexpr int G = kEpiGroups;
       uint32_t da[32], db[32];
       if (eg < nslab) tmem_ld32(tbase + eg * 32, da);
-      for (int sl = eg; sl < nslab; sl += 4) {
+      for (int sl = eg; sl < nslab; sl += 2 * G) {
         tmem_ld_wait();
-        if (sl + 2 < nslab) tmem_ld32(tbase + (sl + 2) * 32, db);
+        if (sl + G < nslab) tmem_ld32(tbase + (sl + G) * 32, db);
         consume(da, sl * 32, min(32, ncols - sl * 32), buf, rs, rb, n0, ncols);
-        if (sl + 2 < nslab) {
+        if (sl + G < nslab) {
           tmem_ld_wait();
-          if (sl + 4 < nslab) tmem_ld32(tbase + (sl + 4) * 32, da);
-          consume(db, (sl + 2) * 32, min(32, ncols - (sl + 2) * 32), buf, rs, rb, n0, ncols);
+          if (sl + 2 * G < nslab) tmem_ld32(tbase + (sl + 2 * G) * 32, da);
+          consume(db, (sl + G) * 32, min(32, ncols - (sl + G) * 32), buf, rs, rb, n0, ncols);
         }
       }
       acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
@@ -383,11 +390,15 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tempty[as]);
     }
-    // fold the two column groups in fixed order: (group 0) + (group 1)
-    if (eg == 1) tail_s.comb[et] = acc64;
+    // fold the column groups in fixed order: ((group 0 + group 1) + group 2) + ...
+    if (eg > 0) tail_s.comb[eg - 1][et] = acc64;
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-    if (eg == 0 && a.partial)
-      a.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * kBM + et] = acc64 + tail_s.comb[et];
+    if (eg == 0 && a.partial) {
+      double tot = acc64;
+#pragma unroll
+      for (int g = 1; g < kEpiGroups; ++g) tot += tail_s.comb[g - 1][et];
+      a.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * kBM + et] = tot;
+    }
   }
 
   tc_fence_before();
@@ -476,6 +487,7 @@ static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st) {
     if (dbg)         ADALOG_LAUNCH_GEMM(MODE_PLAIN, true, false);
     else if (a->cs)  ADALOG_LAUNCH_GEMM(MODE_CS, false, false);
     else if (a->rb)  ADALOG_LAUNCH_GEMM(MODE_RB, false, false);
+    else if (getenv("ADALOG_B200_DIAG_NOEPI")) ADALOG_LAUNCH_GEMM(MODE_NOEPI, false, false);
     else             ADALOG_LAUNCH_GEMM(MODE_PLAIN, false, false);
   }
 #undef ADALOG_LAUNCH_GEMM

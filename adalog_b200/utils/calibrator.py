@@ -74,6 +74,18 @@ class QuantCalibrator:
                 return anc
         return None
 
+    def _is_successor(self, prev, block):
+        """True when `block` directly follows `prev` inside the same nn.Sequential"""
+        if prev is None:
+            return False
+        pn, bn = self._name_of.get(prev), self._name_of.get(block)
+        if pn is None or bn is None:
+            return False
+        pp, _, pi = pn.rpartition('.')
+        bp, _, bi = bn.rpartition('.')
+        return (pp == bp and pi.isdigit() and bi.isdigit() and int(bi) == int(pi) + 1
+                and isinstance(self._by_name.get(pp), torch.nn.Sequential))
+
     def _run_forwards(self, name, device):
         block = self._enclosing_block(name) if self.fast_capture else None
         with torch.no_grad():
@@ -83,13 +95,19 @@ class QuantCalibrator:
                     self.model(inp.to(device))
                 return
             if block is not self._cached_block:
-                grabbed = []
-                h = block.register_forward_pre_hook(lambda m, args: grabbed.append(args[0].detach()))
-                for inp, _ in self.calib_loader:      # this pass also serves the first module of the block
-                    self.model(inp.to(device))
-                h.remove()
-                self._cached_block, self._cached_inputs = block, grabbed
-                return
+                if self._is_successor(self._cached_block, block):
+                    # consecutive children of one nn.Sequential: the next block's input is this block's output under
+                    # the (now final) weights -- exactly what the full forward would recompute
+                    self._cached_inputs = [self._cached_block(x).detach() for x in self._cached_inputs]
+                    self._cached_block = block
+                else:
+                    grabbed = []
+                    h = block.register_forward_pre_hook(lambda m, args: grabbed.append(args[0].detach()))
+                    for inp, _ in self.calib_loader:      # this pass also serves the first module of the block
+                        self.model(inp.to(device))
+                    h.remove()
+                    self._cached_block, self._cached_inputs = block, grabbed
+                    return
             for x in self._cached_inputs:
                 block(x)
 
@@ -113,6 +131,7 @@ class QuantCalibrator:
         """reference calibrator.py:30-67"""
         device = next(self.model.parameters()).device
         self._by_name = dict(self.model.named_modules())
+        self._name_of = {m: n for n, m in self._by_name.items() if isinstance(m, self.block_types)}
         pending = self._pending()
         bar = tqdm(total=len(pending)) if (tqdm is not None and self.progress) else None
         for name, module in self.model.named_modules():
