@@ -34,41 +34,56 @@ __device__ __forceinline__ void uq_fwd(float x, float s, float z, int nl, bool s
   }
 }
 
-// VEC4: n % 4 == 0, pointers 16B aligned and (ngroups == 1 or inner % 4 == 0) so a float4 never straddles groups
-template <bool VEC4>
+// VEC4: n % 4 == 0, pointers 16B aligned and (ngroups == 1 or inner % 4 == 0) so a float4 never straddles groups.
+// Each thread keeps UNR independent 16-byte loads in flight (memory-level parallelism is what this HBM-bound kernel
+// needs); IdxT = uint32_t whenever n < 2^31 so the per-vector group index costs a 32-bit divide.
+template <bool VEC4, typename IdxT>
 __global__ void __launch_bounds__(256) uniform_fakequant_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                int16_t* __restrict__ codes, int64_t n,
                                                                const float* __restrict__ scale,
                                                                const float* __restrict__ zp, int64_t inner,
                                                                int64_t ngroups, int nl, int sym) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool single = ngroups == 1;
-  float s0 = scale[0], z0 = (zp != nullptr) ? zp[0] : 0.0f;
+  const float s0 = scale[0], z0 = (zp != nullptr) ? zp[0] : 0.0f;
   if (VEC4) {
-    const int64_t n4 = n >> 2;
+    constexpr int UNR = 4;
+    const IdxT n4 = (IdxT)(n >> 2);
+    const IdxT inner4 = (IdxT)(inner >> 2), ng = (IdxT)ngroups;
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (; i < n4; i += stride) {
-      float4 v = __ldg(x4 + i);
-      float s = s0, z = z0;
-      if (!single) {
-        int64_t g = ((i << 2) / inner) % ngroups;
-        s = __ldg(scale + g);
-        z = zp ? __ldg(zp + g) : 0.0f;
+    const IdxT stride = (IdxT)gridDim.x * blockDim.x;
+    for (IdxT base = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * UNR) {
+      float4 v[UNR];
+      float sv[UNR], zv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {                      // all loads (data, scale, zero point) issued up front
+        const IdxT i = base + (IdxT)u * stride;
+        sv[u] = s0; zv[u] = z0;
+        if (i < n4) {
+          v[u] = __ldg(x4 + i);
+          if (!single) {
+            const IdxT g = (i / inner4) % ng;
+            sv[u] = __ldg(scale + g);
+            zv[u] = zp ? __ldg(zp + g) : 0.0f;
+          }
+        }
       }
-      float4 o; float c0, c1, c2, c3;
-      uq_fwd(v.x, s, z, nl, sym, o.x, c0);
-      uq_fwd(v.y, s, z, nl, sym, o.y, c1);
-      uq_fwd(v.z, s, z, nl, sym, o.z, c2);
-      uq_fwd(v.w, s, z, nl, sym, o.w, c3);
-      if (y) reinterpret_cast<float4*>(y)[i] = o;
-      if (codes) {
-        short4 cc = make_short4((short)c0, (short)c1, (short)c2, (short)c3);
-        reinterpret_cast<short4*>(codes)[i] = cc;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const IdxT i = base + (IdxT)u * stride;
+        if (i >= n4) break;
+        const float s = sv[u], z = zv[u];
+        float4 o; float c0, c1, c2, c3;
+        uq_fwd(v[u].x, s, z, nl, sym, o.x, c0);
+        uq_fwd(v[u].y, s, z, nl, sym, o.y, c1);
+        uq_fwd(v[u].z, s, z, nl, sym, o.z, c2);
+        uq_fwd(v[u].w, s, z, nl, sym, o.w, c3);
+        if (y) reinterpret_cast<float4*>(y)[i] = o;
+        if (codes) reinterpret_cast<short4*>(codes)[i] = make_short4((short)c0, (short)c1, (short)c2, (short)c3);
       }
     }
   } else {
-    for (; i < n; i += stride) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
       float s = s0, z = z0;
       if (!single) {
         int64_t g = (i / inner) % ngroups;
@@ -86,6 +101,23 @@ __global__ void __launch_bounds__(256) uniform_fakequant_kernel(const float* __r
 // ------------------------------------------------------------------------------------------------
 // K2: log-family fake-quant forward (quantizers/logarithm.py)
 // ------------------------------------------------------------------------------------------------
+// Reference chain (logarithm.py:87-99):  v = clamp(fl((x+shift)/s), 1e-15, 1);  T = fl(fl(-log2f(v)*m1)/m2) with
+// (m1, m2) = (1,1) log2, (2,1) logsqrt2, (37,q) adalog;  c = rint(T);  y = fl(fl(2^-e(c) * f(c)) * s) * [c < 2n] - shift.
+// The dequantised value depends only on the code, so it is tabulated once per CTA (lutv[c], lutv[2n] = 0) with the
+// reference's exact operation order.  EXACT FAST PATH for the code: r = fl(1/s), v' = clamp(x'*r) (within 2 ulp of
+// v), L' = -__log2f(v') (MUFU.LG2: abs error <= 2^-22 on [0.5,2], <= 2 ulp elsewhere), t = L' * fl(m1/m2).  Then
+//   |t - T| <= 2.2e-6 + 6.6e-7 * t   (v' vs v: 3.4e-7*k; LG2: k*2.4e-7 + 2.4e-7 t; log2f 1 ulp: 1.2e-7 t; roundings 3e-7 t)
+// and the check uses m(t) = 5e-6 + 1.5e-6*t: if t is farther than m(t) from every half-integer, rint(t) == c.
+// Otherwise (probability ~1e-4) the element is recomputed with the IEEE chain.  Codes >= 2n read lutv[2n] = 0.
+__device__ __forceinline__ float log_code_exact(float xv, float s, int kind, float qf) {
+  const float v = fminf(fmaxf(__fdiv_rn(xv, s), 1e-15f), 1.0f);
+  const float nlg = -log2f(v);
+  if (kind == 0) return rintf(nlg);
+  if (kind == 1) return rintf(__fmul_rn(nlg, 2.0f));
+  return rintf(__fdiv_rn(__fmul_rn(nlg, 37.0f), qf));
+}
+
+template <bool VEC4>
 __global__ void __launch_bounds__(256) log_fakequant_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            int16_t* __restrict__ codes, int64_t n,
                                                            const float* __restrict__ scale, int kind, int nl,
@@ -93,43 +125,76 @@ __global__ void __launch_bounds__(256) log_fakequant_kernel(const float* __restr
                                                            const float* __restrict__ table1,
                                                            const float* __restrict__ table2,
                                                            const float* __restrict__ shift, int sub_shift) {
-  __shared__ float t1s[256], t2s[256];
+  __shared__ float lutv[260];
   const int ncode = 2 * nl;
-  if (kind == 2) {
-    for (int i = threadIdx.x; i < ncode && i < 256; i += blockDim.x) { t1s[i] = table1[i]; t2s[i] = table2[i]; }
-  }
-  __syncthreads();
   const float s = scale[0];
   const float sh = shift ? shift[0] : 0.0f;
   const float qf = (kind == 2) ? (float)q[0] : 1.0f;
-  const float top = (float)(ncode - 1);
   const float kSqrt2m1 = (float)(1.4142135623730951 - 1.0);  // math.sqrt(2) - 1 cast to FP32 by torch
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float xv = __ldg(x + i);
-    if (shift) xv = __fadd_rn(xv, sh);
-    float v = fminf(fmaxf(__fdiv_rn(xv, s), 1e-15f), 1.0f);
-    float nlg = -log2f(v);
-    float c;
-    if (kind == 0)      c = rintf(nlg);
-    else if (kind == 1) c = rintf(__fmul_rn(nlg, 2.0f));
-    else                c = rintf(__fdiv_rn(__fmul_rn(nlg, 37.0f), qf));
-    const float mask = (c < (float)ncode) ? 1.0f : 0.0f;
-    c = fminf(fmaxf(c, 0.0f), top);
-    float d;
-    if (kind == 0) {
-      d = __fmul_rn(ldexpf(1.0f, -(int)c), s);
-    } else if (kind == 1) {
-      float odd = __fadd_rn(__fmul_rn(fmodf(c, 2.0f), kSqrt2m1), 1.0f);
-      d = __fmul_rn(__fmul_rn(ldexpf(1.0f, -(int)ceilf(__fdiv_rn(c, 2.0f))), odd), s);
-    } else {
-      int ci = (int)c;
-      d = __fmul_rn(__fmul_rn(ldexpf(1.0f, -(int)t1s[ci]), t2s[ci]), s);
+  for (int c = threadIdx.x; c <= ncode && c < 260; c += blockDim.x) {
+    float d = 0.0f;
+    if (c < ncode) {
+      if (kind == 0) {
+        d = __fmul_rn(ldexpf(1.0f, -c), s);
+      } else if (kind == 1) {
+        const float cf = (float)c;
+        const float odd = __fadd_rn(__fmul_rn(fmodf(cf, 2.0f), kSqrt2m1), 1.0f);
+        d = __fmul_rn(__fmul_rn(ldexpf(1.0f, -(int)ceilf(__fdiv_rn(cf, 2.0f))), odd), s);
+      } else {
+        d = __fmul_rn(__fmul_rn(ldexpf(1.0f, -(int)table1[c]), table2[c]), s);
+      }
     }
-    d = __fmul_rn(d, mask);
+    lutv[c] = d;                                             // entry 2n: masked codes
+  }
+  __syncthreads();
+  const float r = __fdiv_rn(1.0f, s);
+  const float kq = (kind == 0) ? 1.0f : (kind == 1 ? 2.0f : __fdiv_rn(37.0f, qf));
+  const float ncf = (float)ncode;
+  auto one = [&](float xin, float& yo, float& co) {
+    const float xv = shift ? __fadd_rn(xin, sh) : xin;
+    const float vp = fminf(fmaxf(__fmul_rn(xv, r), 1e-15f), 1.0f);
+    const float t = fminf(fmaxf(__fmul_rn(-__log2f(vp), kq), 0.0f), ncf);
+    const float tm = __fadd_rn(t, 12582912.0f);
+    float c = __fsub_rn(tm, 12582912.0f);
+    const float f = fabsf(__fsub_rn(t, c));
+    // (the two clamps of v are continuous, so they need no special case; NaN fails the comparison and takes the
+    // IEEE chain like everything near a rounding boundary)
+    if (!(f <= 0.5f - (5e-6f + 1.5e-6f * t))) {
+      c = log_code_exact(xv, s, kind, qf);
+      c = (c < ncf) ? fmaxf(c, 0.0f) : ncf;                  // >= 2n (incl. +inf, NaN): masked entry
+      if (!(c >= 0.0f)) c = ncf;
+    }
+    float d = lutv[(int)c];
     if (sub_shift) d = __fsub_rn(d, sh);
-    if (y) y[i] = d;
-    if (codes) codes[i] = (int16_t)c;
+    yo = d;
+    co = fminf(c, ncf - 1.0f);                               // the reference clamps the stored code to 2n-1
+  };
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (VEC4) {
+    constexpr int UNR = 4;
+    const int64_t n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * UNR) {
+      float4 v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) if (base + u * stride < n4) v[u] = __ldg(x4 + base + u * stride);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t i = base + u * stride;
+        if (i >= n4) break;
+        float4 o; float c0, c1, c2, c3;
+        one(v[u].x, o.x, c0); one(v[u].y, o.y, c1); one(v[u].z, o.z, c2); one(v[u].w, o.w, c3);
+        if (y) reinterpret_cast<float4*>(y)[i] = o;
+        if (codes) reinterpret_cast<short4*>(codes)[i] = make_short4((short)c0, (short)c1, (short)c2, (short)c3);
+      }
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float o, c;
+      one(__ldg(x + i), o, c);
+      if (y) y[i] = o;
+      if (codes) codes[i] = (int16_t)c;
+    }
   }
 }
 
@@ -655,12 +720,15 @@ int adalog_uniform_fakequant_f32(const float* x, float* y, int16_t* codes, int64
                        (reinterpret_cast<uintptr_t>(codes) & 7) == 0;
   const bool vec = aligned && (n % 4 == 0) && (ngroups == 1 || inner % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec)
-    uniform_fakequant_kernel<true><<<grid_for(n / 4, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner, ngroups,
-                                                                        n_levels, symmetric);
+  if (vec && n < (1ll << 31))
+    uniform_fakequant_kernel<true, uint32_t><<<grid_for(n / 16, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
+                                                                                    ngroups, n_levels, symmetric);
+  else if (vec)
+    uniform_fakequant_kernel<true, uint64_t><<<grid_for(n / 16, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
+                                                                                    ngroups, n_levels, symmetric);
   else
-    uniform_fakequant_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner, ngroups,
-                                                                     n_levels, symmetric);
+    uniform_fakequant_kernel<false, uint64_t><<<grid_for(n, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
+                                                                                ngroups, n_levels, symmetric);
   return check_launch("uniform_fakequant");
 }
 
@@ -672,8 +740,14 @@ int adalog_log_fakequant_f32(const float* x, float* y, int16_t* codes, int64_t n
   ADALOG_REQUIRE(kind != 2 || (q && table1 && table2), -1, "log_fakequant: adalog needs q/table1/table2");
   ADALOG_REQUIRE(n_levels <= 128, -1, "log_fakequant: n_levels > 128 unsupported");
   if (n == 0) return 0;
-  log_fakequant_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, codes, n, scale, kind, n_levels, q,
-                                                                          table1, table2, shift, sub_shift);
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(codes) & 7) == 0 && (n % 4 == 0);
+  if (vec)
+    log_fakequant_kernel<true><<<grid_for(n / 16, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, y, codes, n, scale, kind, n_levels, q, table1, table2, shift, sub_shift);
+  else
+    log_fakequant_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, y, codes, n, scale, kind, n_levels, q, table1, table2, shift, sub_shift);
   return check_launch("log_fakequant");
 }
 

@@ -1,0 +1,60 @@
+"""GPU helper (not a pytest file): achieved HBM GB/s of the memory-bound fake-quant kernels vs MEASURED_PEAKS.json.
+Algorithmic bytes = 4 B read + 4 B write per element; CUDA events, 3 warm-ups, tensors > L2."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+from adalog_b200 import ops  # noqa: E402
+import adalog_oracle as O  # noqa: E402
+
+DEV = 'cuda'
+peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(
+    os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
+
+
+def timed(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+res = {}
+x = torch.randn(128, 197, 3072, device=DEV)            # 310 MB: post-GELU-sized activation, > L2
+n = x.numel()
+s1, z1 = torch.tensor([0.05], device=DEV), torch.tensor([7.0], device=DEV)
+ms = timed(lambda: ops.uniform_fakequant(x, s1, z1, 8))
+res['uniform_fakequant per-tensor'] = 8 * n / ms / 1e6
+w = torch.randn(3, 4096, 4096, device=DEV)             # 201 MB weight-like, per-row scale
+sw, zw = torch.rand(3, 4096, 1, device=DEV) * 0.1 + 0.01, torch.randint(0, 16, (3, 4096, 1), device=DEV).float()
+ms = timed(lambda: ops.uniform_fakequant(w, sw, zw, 8))
+res['uniform_fakequant per-row'] = 8 * w.numel() / ms / 1e6
+xg = torch.nn.functional.gelu(x)
+t1, t2 = O.adalog_tables(29, 8)
+q = torch.tensor([29], device=DEV)
+sc, sh = torch.tensor([2.7], device=DEV), torch.tensor([O.SHIFT_GELU], device=DEV)
+ms = timed(lambda: ops.log_fakequant(xg, sc, 2, 8, q, t1.to(DEV), t2.to(DEV), shift=sh, sub_shift=True))
+res['shift_adalog_fakequant'] = 8 * n / ms / 1e6
+p = torch.softmax(torch.randn(128, 12, 197, 197, device=DEV), -1)   # 238 MB
+one = torch.ones(1, 1, 1, 1, device=DEV)
+ms = timed(lambda: ops.log_fakequant(p, one, 2, 8, q, t1.to(DEV), t2.to(DEV)))
+res['adalog_fakequant post-softmax'] = 8 * p.numel() / ms / 1e6
+# the reference's eager chain for comparison (same device)
+ms = timed(lambda: O.uniform_fakequant(x, s1, z1, 8), 3)
+res['reference eager uniform chain (torch)'] = 8 * n / ms / 1e6
+ms = timed(lambda: O.adalog_fakequant(p, one, q, 8, t1, t2), 3)
+res['reference eager adalog chain (torch)'] = 8 * p.numel() / ms / 1e6
+for k, v in res.items():
+    print(f'{k:42s} {v:8.0f} GB/s algorithmic  = {100 * v / peak:5.1f}% of measured HBM peak ({peak:.0f} GB/s)')
+json.dump(dict(peak_gbs=peak, achieved_gbs=res), open(os.path.join(ROOT, 'gpurun_out', 'hbm_probe.json'), 'w'), indent=1)
