@@ -377,6 +377,9 @@ def _fixed_A_operand(ctx, Aq):
     """quant_input_A(A) as a bf16 operand, rows (b,h,s1); returns (Bm, per-head scale FP64 [H])."""
     H = ctx.H
     if getattr(Aq, 'is_log', False):
+        if not hasattr(Aq, 'table2'):
+            raise NotImplementedError("post_softmax_quantizer 'log2' / 'logsqrt2' (fixed-base baselines, reference "
+                                      "matmul.py:307-310) have no device sweep; use 'adalog'")
         nl = Aq.n_levels
         m2 = torch.round(_f32(Aq.table2) * (4 * nl - 2))
         Bm = ops.gen_log_fixed(ctx.A2d, Aq.scale, Aq.q, None, Aq.table1, m2, nl)

@@ -267,3 +267,38 @@ def test_realistic_shapes_sweeps():
     Bq2.scale, Bq2.zero_point = ps.Bq.scale, ps.Bq.zero_point
     qc = torch.arange(10, 138, device=DEV).view(-1, 1, 1, 1, 1)
     assert_sims_close(sweep.matmul_err_A_log_base(pctx, Bq2, qc, 8), ps.sims_A_log_base(qc), 'matmul_err_A_log_base')
+
+
+@pytest.mark.parametrize('eq_n,fpcs', [(64, False), (96, False), (128, False), (64, True)])
+def test_non_default_search_settings(eq_n, fpcs):
+    """eq_n < 128 (candidate rows padded to the 128-lane tile) and the non-FPCS path (fpcs=False: one evaluation per
+    search, reference linear.py:530-534 / :540-542) against the oracle, teacher-forced."""
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden('linear_asym_w4a4'))
+    c = g['cfg']
+    s = O.LinearSearch(g['weight'].clone(), g['bias'].clone(), g['x'].clone(), g['raw_out'].clone(), c['w_bit'],
+                       c['a_bit'], n_V=c['n_V'], calib_batch_size=c['bs'], eq_n=eq_n, search_round=2, steps=4,
+                       fpcs_on=fpcs)
+    s.init_calib()
+    if fpcs:
+        s.steps = 4
+        s.search_round = 2
+        s.search_asym()
+    else:
+        wcs, wcz = O.weight_candidates(s.weight, s.n_V, s.wq.n_levels, eq_n)
+        acs, acz = O.activation_candidates(s.raw_input, s.aq.n_levels, eq_n, False)
+        s.eval_w_self(wcs, wcz)
+        s.eval_a_self(acs, acz)
+        for _ in range(2):
+            s.eval_w(wcs, wcz)
+            s.eval_a(acs, acz)
+    m = QL.AsymmetricallyBatchingQuantLinear(c['in_f'], c['out_f'], bias=True, w_bit=c['w_bit'], a_bit=c['a_bit'],
+                                             calib_batch_size=c['bs'], eq_n=eq_n, fpcs=fpcs, steps=4, search_round=2).to(DEV)
+    m.weight.data.copy_(g['weight'])
+    m.bias.data.copy_(g['bias'])
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(f'eq_n={eq_n} fpcs={fpcs}')
+    assert torch.equal(m.w_quantizer.scale.data, s.wq.scale) and torch.equal(m.a_quantizer.scale.data, s.aq.scale)
+    assert torch.equal(m.w_quantizer.zero_point.data, s.wq.zero_point)
