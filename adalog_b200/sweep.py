@@ -17,7 +17,7 @@ import torch
 from . import ops
 from .utils import dist as adist
 
-WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '768')) << 20
+WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '2048')) << 20
 NUM_SMS = 148
 R_BASE = 37.0
 # uniform x uniform sweeps (every quantizer up to 7 bits: |code - zp| <= 127) run on the INT8 tensor cores
@@ -66,14 +66,21 @@ def _side_streams(device):
     return _side[key]
 
 
-def _launch_plan(nu, ug, NT):
-    """static CTA partition of one launch: (units per CTA, CTAs per group, N-tile splits)"""
+L2_SLICE_BYTES = 32 << 20     # fixed-operand slice that concurrently running CTAs should share out of the 126 MB L2
+
+
+def _launch_plan(nu, ug, NT, b_bytes_per_group=0):
+    """static CTA partition of one launch: (units per CTA, CTAs per group, N-tile splits).
+
+    CTAs of one N split walk the same fixed-operand rows at the same time (blockIdx.x is the fast grid axis), so the
+    rows are fetched from HBM once and then served by L2 -- provided one split's slice fits: enough splits are made
+    that it does (matters for K=3072 weight sweeps, where the whole operand is 155 MB)."""
     groups = nu // ug
     want = max(NUM_SMS, min(NUM_SMS * 4, (nu * NT) // 8))
     upc = min(ug, max(1, math.ceil(nu / want)))
     cpg = math.ceil(ug / upc)
-    S = min(NT, max(1, round(want / (groups * cpg))))
-    return groups, upc, cpg, S
+    S = max(1, round(want / (groups * cpg)), math.ceil(b_bytes_per_group / L2_SLICE_BYTES))
+    return groups, upc, cpg, min(NT, S)
 
 
 def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=1, rs_mod=1, cs=None, cb=None,
@@ -101,7 +108,7 @@ def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=
 
     def gemm(u0, nu, buf):
         ug = nu if single else UG
-        groups, upc, cpg, S = _launch_plan(nu, ug, NT)
+        groups, upc, cpg, S = _launch_plan(nu, ug, NT, N * ka * (1 if i8 else 2))
         part = ops.cand_gemm_err(buf, nu * ops.P_TILE, Bm, ka, N, nu, ug, brpg, 0 if single else u0 // UG, u0, y,
                                  u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN, k_true, i8)
         return part.view(S, groups, cpg, ops.P_TILE).sum(dim=(0, 2))

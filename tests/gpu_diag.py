@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 from adalog_b200 import ops, sweep  # noqa: E402
 
 DEV = 'cuda'
+PROBE_FROM = int(os.environ.get('PROBE_FROM', '0'))
 
 
 def probe_tile():
@@ -69,7 +70,8 @@ def perf_probe():
     from adalog_b200.quantizers import UniformQuantizer
     import adalog_oracle as O
     for (Bn, T, D, Do, tag) in ((128, 197, 384, 1152, 'DeiT-S qkv'), (128, 197, 384, 384, 'DeiT-S proj'),
-                                (128, 197, 1536, 384, 'DeiT-S fc2-shaped'), (128, 197, 768, 768, 'DeiT-B proj')):
+                                (128, 197, 1536, 384, 'DeiT-S fc2-shaped'), (128, 197, 768, 768, 'DeiT-B proj'),
+                                (128, 197, 3072, 768, 'DeiT-B fc2-shaped'))[PROBE_FROM:]:
         torch.manual_seed(0)
         x = torch.randn(Bn, T, D, device=DEV)
         W = torch.randn(Do, D, device=DEV) * 0.02
