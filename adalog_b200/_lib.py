@@ -21,6 +21,7 @@ class GemmErrArgs(ctypes.Structure):
         ('A', c_vp), ('Bm', c_vp), ('a_rows', c_i64), ('b_rows', c_i64),
         ('KB', ctypes.c_int32), ('N', ctypes.c_int32), ('BN', ctypes.c_int32), ('U', ctypes.c_int32),
         ('UG', ctypes.c_int32), ('upc', ctypes.c_int32), ('S', ctypes.c_int32), ('dtype', ctypes.c_int32),
+        ('order', ctypes.c_int32), ('reserved', ctypes.c_int32),
         ('brpg', c_i64), ('g_base', c_i64), ('u_base', c_i64),
         ('y', c_vp), ('ldy', c_i64),
         ('rs', c_vp), ('rb', c_vp), ('rs_div', c_i64), ('rs_mod', c_i64),

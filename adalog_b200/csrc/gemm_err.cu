@@ -73,7 +73,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((it & 0xff) == 0xff) {
       if (t0 == 0) t0 = clock64();
       else if (clock64() - t0 > 4000000000ll) {  // ~2 s
-        printf("adalog gemm_err: mbarrier timeout (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+        printf("adalog gemm_err: mbarrier timeout (block %d,%d thread %d parity %u)\n", blockIdx.x, 0,
                threadIdx.x, parity);
         __trap();
       }
@@ -150,6 +150,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 struct KArgs {
   int KB, N, BN, NT, U, UG, upc, cpg;
+  int gx, S, split_fast;   // logical grid (gx unit lists x S N-tile splits) laid out on a 1-D launch
   long long brpg, g_base, u_base;
   const float* y; long long ldy;
   const float* rs; const float* rb; long long rs_div, rs_mod;
@@ -176,13 +177,18 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // static work list of this CTA
-  const int g_local = blockIdx.x / a.cpg;
-  const int ci = blockIdx.x - g_local * a.cpg;
-  const int u0 = g_local * a.UG + ci * a.upc;
-  const int u1 = min(min(u0 + a.upc, (g_local + 1) * a.UG), a.U);
-  const int nt0 = (int)(((long long)blockIdx.y * a.NT) / gridDim.y);
-  const int nt1 = (int)(((long long)(blockIdx.y + 1) * a.NT) / gridDim.y);
+  // static work list of this CTA.  Logical coordinates (bx = unit list, by = N-tile split) come off a 1-D grid in
+  // one of two orders: unit-fast (co-resident CTAs walk the same fixed-operand tiles: those stay in L2) or
+  // split-fast (the S CTAs that share one unit list are co-resident: the candidate operand is fetched once).
+  const int bx = a.split_fast ? (int)(blockIdx.x / a.S) : (int)(blockIdx.x % a.gx);
+  const int by = a.split_fast ? (int)(blockIdx.x % a.S) : (int)(blockIdx.x / a.gx);
+  const int g_local = bx / a.cpg;
+  const int ci = bx - g_local * a.cpg;
+  // the UG units of a group are dealt evenly to its cpg CTAs (sizes differ by at most one)
+  const int u0 = g_local * a.UG + (int)(((long long)ci * a.UG) / a.cpg);
+  const int u1 = min(g_local * a.UG + (int)(((long long)(ci + 1) * a.UG) / a.cpg), a.U);
+  const int nt0 = (int)(((long long)by * a.NT) / a.S);
+  const int nt1 = (int)(((long long)(by + 1) * a.NT) / a.S);
   const int n_units = max(u1 - u0, 0);
   const int n_nt = nt1 - nt0;
   const int n_tiles = n_units * n_nt;
@@ -397,7 +403,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       double tot = acc64;
 #pragma unroll
       for (int g = 1; g < kEpiGroups; ++g) tot += tail_s.comb[g - 1][et];
-      a.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * kBM + et] = tot;
+      a.partial[((long long)by * a.gx + bx) * kBM + et] = tot;
     }
   }
 
@@ -447,6 +453,7 @@ static int validate(const adalog_gemm_err_args* a, bool need_partial) {
                  "cand_gemm_err: non-positive size");
   ADALOG_REQUIRE(a->BN >= 16 && a->BN <= kMaxBN && a->BN % 16 == 0, -1, "cand_gemm_err: BN must be a multiple of 16 in [16,256]");
   ADALOG_REQUIRE(a->dtype == ADALOG_BF16 || a->dtype == ADALOG_I8, -1, "cand_gemm_err: dtype must be ADALOG_BF16 or ADALOG_I8");
+  ADALOG_REQUIRE(a->order == ADALOG_ORDER_UNIT_FAST || a->order == ADALOG_ORDER_SPLIT_FAST, -1, "cand_gemm_err: bad order");
   ADALOG_REQUIRE(a->U % a->UG == 0, -1, "cand_gemm_err: U must be a multiple of UG");
   ADALOG_REQUIRE(a->a_rows >= (int64_t)a->U * kBM, -1, "cand_gemm_err: A has fewer than U*128 rows");
   ADALOG_REQUIRE(a->rs_div > 0 && a->rs_mod > 0 && a->rs, -1, "cand_gemm_err: row scale required");
@@ -471,7 +478,8 @@ static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st) {
   if (rc) return rc;
   rc = make_map(&tmB, a->Bm, a->b_rows, cols, a->BN, i8);
   if (rc) return rc;
-  dim3 grid((unsigned)((a->U / a->UG) * k.cpg), (unsigned)a->S);
+  k.gx = (a->U / a->UG) * k.cpg; k.S = a->S; k.split_fast = a->order == ADALOG_ORDER_SPLIT_FAST;
+  dim3 grid((unsigned)((long long)k.gx * k.S));
 #define ADALOG_LAUNCH_GEMM(MD, DBG, I8)                                                                       \
   do {                                                                                                        \
     cudaFuncSetAttribute(cand_gemm_err_kernel<MD, DBG, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \

@@ -238,6 +238,26 @@ __device__ __forceinline__ float uq_int_fast(float x, const float4 c, bool& unsa
   return tc;
 }
 
+// Generator form of the same fast path, arranged for the FMA pipe (the generators were ALU-pipe bound on compares
+// and min/max).  c = {r/2n, zp/2n, L/2n, 1.5*2^23 - zp} with r = fl(1/s), L = 2n-1; 2n is a power of two, so
+//   ts = sat(fma(x, r/2n, zp/2n))          == clamp(fl(x*r + zp), 0, 2n) / 2n      (FFMA.SAT: the clamp is free)
+//   ts = min(ts, L/2n)                                                               (the one FMNMX left)
+//   tm = fma(ts, 2n, 1.5*2^23 - zp)        == rint(clamped) - zp + 1.5*2^23         (code - zp in the low mantissa bits)
+//   d  = fma(ts, 2n, -(tm - (1.5*2^23 - zp))) == clamped - rint(clamped)
+// fl(x*r + zp) is within 0.5 ulp(256) + |x/s| 2^-24 <= 2.3e-5 of x/s + zp and the reference's fl(x/s) within 1.6e-5 of
+// x/s (0 <= zp <= L <= 255, so |x/s| <= 255 wherever the clamp does not decide), so with |d| <= 0.5 - 2^-14 both round
+// to the same integer; where the clamp decides d == 0.  Candidates with a zero point that is not an integer in [0, L]
+// carry thr < 0 and always take the IEEE path; +-inf saturate like the reference's clamp; NaN (FFMA.SAT returns 0 for
+// it) is caught per chunk by the caller.
+__device__ __forceinline__ float uq_code_fast(float x, const float4 c, float two_n, float thr, bool& unsafe) {
+  float ts = __saturatef(fmaf(x, c.x, c.y));
+  ts = fminf(ts, c.z);
+  const float tm = fmaf(ts, two_n, c.w);
+  const float d = fmaf(ts, two_n, -__fsub_rn(tm, c.w));
+  unsafe |= !(fabsf(d) <= thr);
+  return tm;                               // (code - zp) + 1.5*2^23
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: weight self-error sweep (linear.py:296-309).  One CTA per weight row, one thread per candidate.
 // ------------------------------------------------------------------------------------------------
@@ -347,6 +367,12 @@ __device__ __forceinline__ uint32_t pack_i8x4(float a, float b, float c, float d
   return __byte_perm(__byte_perm(ua, ub, 0x0040), __byte_perm(uc, ud, 0x0040), 0x5410);
 }
 
+// same, for values that already carry the 1.5*2^23 offset
+__device__ __forceinline__ uint32_t pack_i8x4_bits(float a, float b, float c, float d) {
+  return __byte_perm(__byte_perm(__float_as_uint(a), __float_as_uint(b), 0x0040),
+                     __byte_perm(__float_as_uint(c), __float_as_uint(d), 0x0040), 0x5410);
+}
+
 __device__ __forceinline__ void store8(uint16_t* dst, const float (&v)[8]) {
   uint4 o;
   o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -403,18 +429,23 @@ __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __re
   constexpr int EPT = I8 ? 16 : 8;         // elements per thread chunk = one 16-byte store
   constexpr int ESZ = I8 ? 1 : 2;
   uint8_t* out = reinterpret_cast<uint8_t*>(out_v);
-  __shared__ float4 cand[ADALOG_P];
+  __shared__ float4 cand[ADALOG_P];        // {r/2n, zp/2n, L/2n, 1.5*2^23 - zp}
+  __shared__ float2 cand_sz[ADALOG_P];     // {s, zp}: IEEE path
+  __shared__ float cthr[ADALOG_P];         // 0.5 - 2^-14, or -1 when the candidate must take the IEEE path
   __shared__ float rsum[ADALOG_P];
   const int64_t u = blockIdx.x;
   const int64_t g = ((u_base + u) / g_div) % g_mod;
   const float L = (float)(2 * nl - 1);
+  const float two_n = (float)(2 * nl);
   for (int p = threadIdx.x; p < ADALOG_P; p += blockDim.x) {
     const int pp = min(p, P - 1);          // pad rows repeat the last candidate
     const float s = __ldg(cs + pp * pstride + g * gstride);
     const float z = __ldg(cz + pp * pstride + g * gstride);
-    float r = __fdiv_rn(1.0f, s);
-    if (z != rintf(z)) r = __int_as_float(0x7fc00000);   // non-integer zero point: always take the IEEE path
-    cand[p] = make_float4(r, -z, L - z, s);
+    const float r = __fdiv_rn(1.0f, s);
+    const bool fast = z == rintf(z) && z >= 0.0f && z <= L && r == r && fabsf(r) <= 3.0e38f;
+    cand[p] = make_float4(r / two_n, z / two_n, L / two_n, kMagic - z);
+    cand_sz[p] = make_float2(s, z);
+    cthr[p] = fast ? kFracSafe : -1.0f;
     rsum[p] = 0.0f;
   }
   __syncthreads();
@@ -431,32 +462,44 @@ __global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __re
     const int kc = ch * EPT;
     const bool tail = kc + EPT > K;
     float xv[EPT];
+    int nan_flag = 0;
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) xv[j] = (kc + j < K) ? __ldg(xrow + kc + j) : 0.0f;
+    for (int j = 0; j < EPT; ++j) {
+      xv[j] = (kc + j < K) ? __ldg(xrow + kc + j) : 0.0f;
+      nan_flag |= (xv[j] != xv[j]) ? 1 : 0;
+    }
+    asm volatile("" : "+r"(nan_flag));     // one register test per candidate, not EPT re-compares
     uint8_t* dst = out + (u * ADALOG_P + p_lo + pg) * pitch + (int64_t)kc * ESZ;
-    const float4* cp = cand + p_lo + pg;
-    for (int it = 0; it < iters; ++it, dst += dstep, cp += npg) {
-      const float4 c = *cp;
-      float v[EPT];
-      bool unsafe = false;
+    int p = p_lo + pg;
+    for (int it = 0; it < iters; ++it, dst += dstep, p += npg) {
+      const float4 c = cand[p];
+      const float thr = cthr[p];
+      float tm[EPT], v[EPT];
+      bool unsafe = nan_flag != 0;
 #pragma unroll
-      for (int j = 0; j < EPT; ++j) v[j] = uq_int_fast(xv[j], c, unsafe);
-      if (unsafe) {                                      // a few % of warps: redo the chunk on the IEEE path
+      for (int j = 0; j < EPT; ++j) tm[j] = uq_code_fast(xv[j], c, two_n, thr, unsafe);
+      if (unsafe) {                                      // rare: redo the chunk on the IEEE path
+        const float2 sz = cand_sz[p];
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) v[j] = uq_int(xv[j], c.w, -c.y, c.z - c.y);
+        for (int j = 0; j < EPT; ++j) tm[j] = __fadd_rn(uq_int(xv[j], sz.x, sz.y, L), kMagic);
       }
       if (tail) {
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) if (kc + j >= K) v[j] = 0.0f;
+        for (int j = 0; j < EPT; ++j) if (kc + j >= K) tm[j] = kMagic;
       }
       uint4 o;
-      if (I8) {
-        o.x = pack_i8x4(v[0], v[1], v[2], v[3]);   o.y = pack_i8x4(v[4], v[5], v[6], v[7]);
-        o.z = pack_i8x4(v[8 % EPT], v[9 % EPT], v[10 % EPT], v[11 % EPT]);
-        o.w = pack_i8x4(v[12 % EPT], v[13 % EPT], v[14 % EPT], v[15 % EPT]);
-      } else {
+      if (I8) {                                          // low mantissa byte of (v + 1.5*2^23) = v as int8
+        o.x = pack_i8x4_bits(tm[0], tm[1], tm[2], tm[3]);   o.y = pack_i8x4_bits(tm[4], tm[5], tm[6], tm[7]);
+        o.z = pack_i8x4_bits(tm[8 % EPT], tm[9 % EPT], tm[10 % EPT], tm[11 % EPT]);
+        o.w = pack_i8x4_bits(tm[12 % EPT], tm[13 % EPT], tm[14 % EPT], tm[15 % EPT]);
+      }
+      if (!I8 || ROWSUM) {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) v[j] = __fsub_rn(tm[j], kMagic);
+      }
+      if (!I8) {
         o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        o.z = pack_bf16x2(v[4 % EPT], v[5 % EPT]); o.w = pack_bf16x2(v[6 % EPT], v[7 % EPT]);
       }
 #pragma unroll
       for (int rep = 0; rep < KREP; ++rep) *reinterpret_cast<uint4*>(dst + (int64_t)rep * kpad * ESZ) = o;
@@ -512,9 +555,10 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
                                                               const long long* __restrict__ cq, int P,
                                                               const float* __restrict__ shift,
                                                               const float* __restrict__ mtab, int nl,
-                                                              uint16_t* __restrict__ out, int kpad, int tpc) {
+                                                              uint16_t* __restrict__ out, int kpad, int tpc, uint32_t magic4) {
   extern __shared__ float lut[];           // [per][2n + 1]
-  __shared__ float4 cand[ADALOG_P];        // {mul, off, lim, q}
+  __shared__ float4 cand[ADALOG_P];        // {mul / 2n, off / 2n, lim, mul}
+  __shared__ float candq[ADALOG_P];
   __shared__ float chalf[ADALOG_P];        // 0.5 - candidate part of the rounding margin
   __shared__ float cscale[ADALOG_P];
   __shared__ float mt[64];
@@ -544,7 +588,8 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
       lim = __int_as_float(0x7f800000);
       hp = 6.103515625e-05f;
     }
-    cand[p] = make_float4(mul, off, lim, qf);
+    cand[p] = make_float4(mul / ncode, off / ncode, lim, mul);
+    candq[p] = qf;
     chalf[p] = 0.5f - hp;
     cscale[p] = s;
   }
@@ -554,7 +599,7 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
     const int pi = i / lw, c = i - pi * lw;
     float val = 0.0f;
     if (c < ncode_i) {
-      const int cqi = c * (int)cand[p_lo + pi].w;
+      const int cqi = c * (int)candq[p_lo + pi];
       const int e = cqi / 37;
       if (e <= 120) val = ldexpf(mt[cqi - e * 37], -e);
     }
@@ -574,7 +619,9 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
   const int iters = (per - pg + npg - 1) / npg;
   const float* xrow = x + u * ldx;
   // shared address of lut[0][0] minus the magic-number offset: addr = bits(t + 1.5*2^23) * 4 + lut_bias (mod 2^32)
-  const uint32_t lut_bias = (uint32_t)__cvta_generic_to_shared(lut) - 0x2D000000u;
+  // (magic4 = bits(1.5*2^23) * 4 mod 2^32 arrives as a kernel argument: as a literal, ptxas re-splits it out of the
+  // row address and spends an extra add per element on it)
+  const uint32_t lut_bias = (uint32_t)__cvta_generic_to_shared(lut) - magic4;
   for (int ch = lane_chunk; ch < cpr; ch += tpc) {
     const int kc = ch << 3;
     const bool tail = kc + 8 > K;
@@ -592,25 +639,31 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
     }
     uint16_t* dst = out + (u * ADALOG_P + p_lo + pg) * (int64_t)kpad + kc;
     int p = p_lo + pg;
+    // keep the chunk's clamp flag in a register: the compiler otherwise re-derives it from lx[] per candidate
+    int clamp_flag = clamp_region ? 1 : 0;
+    asm volatile("" : "+r"(clamp_flag));
     for (int it = 0; it < iters; ++it, dst += dstep, p += npg) {
-      const float4 c = cand[p];
+      const float4 c = cand[p];          // {mul / 2n, off / 2n, lim, q}: 2n is a power of two, the scaling is exact
       const float half = chalf[p];
-      const uint32_t row = lut_bias + (uint32_t)((p - p_lo) * lw) * 4u;
+      uint32_t row = lut_bias + (uint32_t)((p - p_lo) * lw) * 4u;
+      asm volatile("" : "+r"(row));      // one add per element below, not a re-derivation of the row address
       float v[8];
-      bool unsafe = clamp_region;
+      bool unsafe = clamp_flag != 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float t = fminf(fmaxf(fmaf(e1[j], c.x, c.y), 0.0f), ncode);   // codes >= 2n all read lut[2n] = 0
-        const float tm = __fadd_rn(t, kMagic);
-        const float f = fabsf(__fsub_rn(t, __fsub_rn(tm, kMagic)));
-        unsafe |= !(f <= fmaf(-gm[j], c.x, half));
+        // t/2n clamped to [0,1] by the FMA's own saturation (codes >= 2n all read lut[2n] = 0), then
+        // tm = t + 1.5*2^23 in one more FMA: same roundings as fma -> clamp -> add, two ALU-pipe min/max fewer
+        const float ts = __saturatef(fmaf(e1[j], c.x, c.y));
+        const float tm = fmaf(ts, ncode, kMagic);
+        const float d = fmaf(ts, ncode, -__fsub_rn(tm, kMagic));
+        unsafe |= !(fabsf(d) <= fmaf(-gm[j], c.w, half));
         float val;
         asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(__float_as_uint(tm) * 4u + row));
         v[j] = val;
       }
       if (unsafe) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = log_value_slow(xs[j], lx[j], SCALED, cscale[p], c.w, mt, ncode);
+        for (int j = 0; j < 8; ++j) v[j] = log_value_slow(xs[j], lx[j], SCALED, cscale[p], candq[p], mt, ncode);
       }
       if (tail) {
 #pragma unroll
@@ -836,10 +889,10 @@ int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const flo
   const size_t lut_bytes = (size_t)(ADALOG_P / grid.y) * (2 * n_levels + 1) * sizeof(float);
   if (cs)
     gen_log_cand_lut_kernel<true><<<grid, tpc * npg, lut_bytes, st>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
-                                                                      out, kpad, tpc);
+                                                                      out, kpad, tpc, 0x2D000000u);
   else
     gen_log_cand_lut_kernel<false><<<grid, tpc * npg, lut_bytes, st>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
-                                                                       out, kpad, tpc);
+                                                                       out, kpad, tpc, 0x2D000000u);
   return check_launch("gen_log_cand");
 }
 

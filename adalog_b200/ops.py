@@ -234,14 +234,16 @@ def pick_bn(N):
 
 
 def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, ldy, rs, rb, rs_div, rs_mod, cs, cb,
-                  upc, S, BN=None, k_true=None, i8=False):
-    """One launch of adalog_cand_gemm_err.  Returns FP64 partial [S, gridX, 128].  ka: operand pitch in elements."""
+                  upc, S, BN=None, k_true=None, i8=False, split_fast=False):
+    """One launch of adalog_cand_gemm_err.  Returns FP64 partial [S, gridX, 128].  ka: operand pitch in elements.
+    split_fast only changes which CTAs are co-resident (L2 reuse), never a result bit."""
     BN = BN or pick_bn(N)
     a = GemmErrArgs()
     a.A, a.Bm = A.data_ptr(), Bm.data_ptr()
     a.a_rows, a.b_rows = int(a_rows), int(Bm.shape[0])
     a.KB = ka // (2 * BK if i8 else BK)
     a.dtype = I8 if i8 else BF16
+    a.order = 1 if split_fast else 0
     a.N, a.BN, a.U, a.UG, a.upc, a.S = int(N), int(BN), int(U), int(UG), int(upc), int(S)
     a.brpg, a.g_base, a.u_base = int(brpg), int(g_base), int(u_base)
     a.y, a.ldy = y.data_ptr() + 4 * int(y_off), int(ldy)

@@ -9,6 +9,7 @@ Factorisation used by every GEMM sweep: fake-quantised ope
 (integer) x scale, so the tensor cores multiply the exact integer parts in bf16 with FP32 accumulation
 and the scales, biases and shift corrections are applied in the fused epilogue.
 """
+import functools
 import math
 import os
 
@@ -67,20 +68,49 @@ def _side_streams(device):
 
 
 L2_SLICE_BYTES = 32 << 20     # fixed-operand slice that concurrently running CTAs should share out of the 126 MB L2
+L2_CAND_BYTES = 48 << 20      # candidate-operand bytes that co-resident CTAs may hold before L2 starts to thrash
+L2_CAND_TARGET = 16 << 20
+CTA_FIXED_COST = 8000        # prologue + pipeline fill + epilogue drain of one CTA, SM clocks (~4 us)
 
 
-def _launch_plan(nu, ug, NT, b_bytes_per_group=0):
-    """static CTA partition of one launch: (units per CTA, CTAs per group, N-tile splits).
+@functools.lru_cache(maxsize=4096)
+def _launch_plan(nu, ug, NT, b_bytes_per_group=0, unit_bytes=0, tile_cost=16384):
+    """static CTA partition of one launch: (groups, units per CTA, CTAs per group, N-tile splits, split_fast).
 
-    CTAs of one N split walk the same fixed-operand rows at the same time (blockIdx.x is the fast grid axis), so the
-    rows are fetched from HBM once and then served by L2 -- provided one split's slice fits: enough splits are made
-    that it does (matters for K=3072 weight sweeps, where the whole operand is 155 MB)."""
+    L2 residency.  A CTA re-reads its unit's 128 candidate rows (unit_bytes) once per N tile, and all CTAs walk the
+    fixed operand.  Which of the two stays in the 126 MB L2 depends on who is co-resident:
+    * unit-fast order (default): neighbours hold different units and walk the same fixed-operand tiles at the same
+      time, so those are fetched from HBM once -- provided one split's slice fits (enough splits are made that it
+      does), and provided 148 units of candidate rows fit beside it;
+    * split-fast order: for K >= 1536 they do not (148 x 786 KB at K=3072: ncu showed 2.7x the algorithmic DRAM
+      reads), so the S CTAs that share one unit list are made neighbours instead: the unit's rows are fetched once
+      and hit L2 for the other S-1 splits, and the ~148/S units that are co-resident still share fixed tiles.
+
+    Wave quantisation.  All CTAs of a launch do equal work, so the launch takes ceil(CTAs / 148) rounds of the
+    largest CTA; among the partitions the L2 rules allow, the one minimising rounds x (tiles per CTA x tile_cost +
+    fixed CTA cost) is taken (tile_cost in SM clocks: the larger of the tile's MMA time and its 8 x BN TMEM read-out)."""
     groups = nu // ug
-    want = max(NUM_SMS, min(NUM_SMS * 4, (nu * NT) // 8))
-    upc = min(ug, max(1, math.ceil(nu / want)))
-    cpg = math.ceil(ug / upc)
-    S = max(1, round(want / (groups * cpg)), math.ceil(b_bytes_per_group / L2_SLICE_BYTES))
-    return groups, upc, cpg, min(NT, S)
+    s_min, split_fast = min(NT, max(1, math.ceil(b_bytes_per_group / L2_SLICE_BYTES))), False
+    if NT > 1 and unit_bytes * min(NUM_SMS, nu) > L2_CAND_BYTES:
+        split_fast = True
+        s_min = min(NT, max(s_min, math.ceil(unit_bytes * NUM_SMS / L2_CAND_TARGET)))
+    best = None
+    for S in range(s_min, min(NT, max(s_min, 16)) + 1):
+        tps = math.ceil(NT / S)
+        cands = {ug, 1}
+        for w in range(1, 9):
+            c = (NUM_SMS * w) // (groups * S)
+            if c >= 1:
+                cands.add(math.ceil(ug / min(c, ug)))
+        for upc in cands:
+            cpg = math.ceil(ug / upc)
+            ctas = groups * cpg * S
+            cost = math.ceil(ctas / NUM_SMS) * (math.ceil(ug / cpg) * tps * tile_cost + CTA_FIXED_COST)
+            key = (cost, ctas)
+            if best is None or key < best[0]:
+                best = (key, upc, cpg, S)
+    _, upc, cpg, S = best
+    return groups, upc, cpg, S, split_fast
 
 
 def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=1, rs_mod=1, cs=None, cb=None,
@@ -108,9 +138,10 @@ def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=
 
     def gemm(u0, nu, buf):
         ug = nu if single else UG
-        groups, upc, cpg, S = _launch_plan(nu, ug, NT, N * ka * (1 if i8 else 2))
+        groups, upc, cpg, S, sf = _launch_plan(nu, ug, NT, N * ka * (1 if i8 else 2), unit_elems,
+                                               max((ka // 64) * BN * (1 if i8 else 2), 8 * BN))
         part = ops.cand_gemm_err(buf, nu * ops.P_TILE, Bm, ka, N, nu, ug, brpg, 0 if single else u0 // UG, u0, y,
-                                 u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN, k_true, i8)
+                                 u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN, k_true, i8, sf)
         return part.view(S, groups, cpg, ops.P_TILE).sum(dim=(0, 2))
 
     outs = []

@@ -32,6 +32,8 @@ extern "C" {
 #define ADALOG_BK 64          /* bf16 elements per 128-byte swizzled K block (128 for int8 operands) */
 #define ADALOG_BF16 0         /* operand dtype: bf16 (any quantizer; exact for |int| <= 256 and m*2^-e) */
 #define ADALOG_I8 1           /* operand dtype: int8 (uniform quantizers up to 7 bits; tcgen05 kind::i8, S32 accumulate) */
+#define ADALOG_ORDER_UNIT_FAST 0   /* CTA order: neighbours differ in unit list (share fixed-operand tiles through L2) */
+#define ADALOG_ORDER_SPLIT_FAST 1  /* CTA order: neighbours differ in N split (share one unit's candidate rows through L2) */
 
 int adalog_version(void);
 const char* adalog_last_error(void);
@@ -114,8 +116,9 @@ int adalog_gen_split3(const float* x, int64_t R, int K, int64_t ldx, uint16_t* o
  * D[p, n] = sum_k A[u*128+p, k] * Bm[g*brpg + n, k]   (tcgen05.mma kind::f16 -> FP32, or kind::i8 -> S32, in TMEM)
  * yhat    = rs[ri+p] * (cs ? cs[n]*D : D) + (rb ? rb[ri+p] : 0),  ri = ((u_base+u)/rs_div % rs_mod)*128
  * e[p]   += (y[u*ldy + n] - (cb ? cb[n] : 0) - yhat)^2      summed over the CTA's units and N tiles
- * partial[(blockIdx.y*gridDim.x + blockIdx.x)*128 + p] = e[p] (FP64).  gridDim = (G_chunk * cpg, S):
- * CTA x handles units [g*UG + ci*upc, +upc) of group g = x / cpg, ci = x % cpg; CTA y handles N tiles
+ * partial[(y*gridX + x)*128 + p] = e[p] (FP64).  Logical grid = (gridX = G_chunk * cpg, S), launched 1-D in `order`:
+ * CTA x handles units [g*UG + ci*UG/cpg, g*UG + (ci+1)*UG/cpg) of group g = x / cpg, ci = x % cpg, cpg = ceil(UG/upc);
+ * CTA y handles N tiles
  * [y*NT/S, (y+1)*NT/S).  The partition is static, so equal candidates produce bit-equal sums. */
 typedef struct {
   const void* A;      const void* Bm;
@@ -125,9 +128,11 @@ typedef struct {
   int32_t BN;         /* tile width, multiple of 16, <= 256 */
   int32_t U;          /* units in this launch */
   int32_t UG;         /* units per group */
-  int32_t upc;        /* units per CTA */
+  int32_t upc;        /* units per CTA (upper bound: a group is dealt evenly to ceil(UG/upc) CTAs) */
   int32_t S;          /* N-tile splits */
   int32_t dtype;      /* ADALOG_BF16 | ADALOG_I8 */
+  int32_t order;      /* ADALOG_ORDER_*: which CTAs are co-resident; does not change any result bit */
+  int32_t reserved;   /* 0 */
   int64_t brpg;       /* Bm rows per group */
   int64_t g_base;     int64_t u_base;
   const float* y;     int64_t ldy;

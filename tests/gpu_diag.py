@@ -102,6 +102,15 @@ def perf_probe():
             tl = timed(lambda: sweep.linear_err_log(gctx, W.view(1, Do, D), b, wq, lq, sc, qc))
             tlw = timed(lambda: sweep.linear_err_w(gctx, W.view(1, Do, D), b, lq, cs, cz, 8))
             print(f'{tag}: log A-sweep {tl:.2f} ms ({flops / tl / 1e9:.0f} TFLOP/s)  W-sweep(log act) {tlw:.2f} ms')
+            for nm, fn in (('log A-sweep', lambda: sweep.linear_err_log(gctx, W.view(1, Do, D), b, wq, lq, sc, qc)),
+                           ('W-sweep(log act)', lambda: sweep.linear_err_w(gctx, W.view(1, Do, D), b, lq, cs, cz, 8)),
+                           ('A-sweep', lambda: sweep.linear_err_a(ctx, W.view(1, Do, D), b, wq, acs, acz, 8))):
+                ops.profile_reset(True)
+                t = timed(fn, 2)
+                fl, ms, n = ops.profile_gemm_summary()
+                ops.profile_reset(False)
+                print(f'   {nm}: {t:.2f} ms; GEMM kernel {ms / 3:.2f} ms in {n // 3} launches ({fl / ms / 1e9:.0f} TFLOP/s); '
+                      f'rest {t - ms / 3:.2f} ms  [overlap={sweep.OVERLAP}]')
 
 
 def perf_matmul():

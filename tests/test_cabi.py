@@ -32,5 +32,5 @@ def test_binding_covers_header():
 
 
 def test_struct_layout_matches_header():
-    # adalog_gemm_err_args: 2 ptr + 2 i64 + 8 i32 + 3 i64 + ptr + i64 + 2 ptr + 2 i64 + 2 ptr + ptr
-    assert ctypes.sizeof(_lib.GemmErrArgs) == 8 * 4 + 4 * 8 + 8 * 3 + 8 * 2 + 8 * 2 + 8 * 2 + 8 * 2 + 8
+    # adalog_gemm_err_args: 2 ptr + 2 i64 + 10 i32 + 3 i64 + ptr + i64 + 2 ptr + 2 i64 + 2 ptr + ptr
+    assert ctypes.sizeof(_lib.GemmErrArgs) == 8 * 4 + 4 * 10 + 8 * 3 + 8 * 2 + 8 * 2 + 8 * 2 + 8 * 2 + 8
