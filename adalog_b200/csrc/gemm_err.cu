@@ -5,8 +5,8 @@
 // accumulated in a register across the CTA's whole static work list with no cross-thread reduction, which
 // keeps equal candidates bit-equal (exact-tie parity, SURVEY.md section 7 hard part 1).
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 4-7 = epilogue (TMEM lanes 32*(w%4)..).  Pipelines: smem full/empty ring (kStages) between TMA and
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2-9 = epilogue (TMEM lanes 32*(w%4)..; two column groups).  Pipelines: smem full/empty ring (kStages) between TMA and
 // MMA; TMEM full/empty (2 accumulator stages of 256 columns) between MMA and epilogue.
 #include "common.cuh"
 #include "../../include/adalog_b200.h"
@@ -24,11 +24,12 @@ constexpr int kAccStages = 2;
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KiB
 constexpr uint32_t kBBytes = kMaxBN * kBK * 2;     // 32 KiB
 constexpr uint32_t kTmemCols = 512;
-constexpr int kEpiWarp0 = 4;            // warps 0-3: TMA producer, MMA issuer + TMEM allocator, two idle
+constexpr int kEpiWarp0 = 2;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM allocator (no idle warps: the registers
+                                        // they would pin are what lets a generator CTA co-reside on the SM)
 constexpr int kEpiWarps = 8;            // two epilogue warps per scheduler (16 was measured slower: register cap + barrier cost)
 constexpr int kEpiGroups = kEpiWarps / 4; // column groups: group g takes the 32-column slabs g, g+G, g+2G, ...
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 384
+constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 320
 
 // barriers and the epilogue's per-tile y / column-scale staging live in STATIC shared memory so that the compiler
 // keeps the shared address space (LDS/STS, not generic LD/ST); the operand ring is dynamic (1024-byte aligned).
@@ -258,12 +259,12 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue: TMEM -> registers -> per-candidate squared error =====================
-    // 8 warps: warp w reads TMEM lanes 32*(w%4)..+31 (candidate p = that lane); group eg = (w-4)/4 takes the 32-column
+    // 8 warps: warp w reads TMEM lanes 32*(w%4)..+31 (candidate p = that lane); group eg = (w-2)/4 takes the 32-column
     // slabs with index == eg (mod 2).  Every candidate therefore has two partial sums, folded in fixed order at the end.
     constexpr bool HAS_CS = MODE == MODE_CS;
     const int ew = warp - kEpiWarp0;
     const int eg = ew >> 2;                                 // column group 0..kEpiGroups-1
-    const int et = ((ew & 3) << 5) | lane;                  // 0..127 = candidate p = TMEM lane
+    const int et = ((warp & 3) << 5) | lane;                // 0..127 = candidate p = TMEM lane (a warp reaches lanes 32*(warp%4)..)
     const int st = threadIdx.x - kEpiWarp0 * 32;            // 0..kEpiThreads-1: staging slot (one y column each)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     double acc64 = 0.0;

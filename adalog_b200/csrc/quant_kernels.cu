@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) gen_uniform_fixed_kernel(const float* __r
 }
 
 template <int KREP, bool ROWSUM, bool I8>
-__global__ void __launch_bounds__(256) gen_uniform_cand_kernel(const float* __restrict__ x, int K, int64_t ldx,
+__global__ void __launch_bounds__(256, 4) gen_uniform_cand_kernel(const float* __restrict__ x, int K, int64_t ldx,
                                                               const float* __restrict__ cs,
                                                               const float* __restrict__ cz, int P, int64_t pstride,
                                                               int64_t gstride, int64_t g_div, int64_t g_mod,

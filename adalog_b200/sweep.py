@@ -63,7 +63,9 @@ _side = {}
 def _side_streams(device):
     key = (device.type, device.index)
     if key not in _side:
-        _side[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        # the GEMM stream has priority: its one-CTA-per-SM grid must get onto the SMs first, the generator's small CTAs
+        # then fill the registers / shared memory it leaves (the other way round the big CTAs never find room)
+        _side[key] = (torch.cuda.Stream(device=device, priority=0), torch.cuda.Stream(device=device, priority=-1))
     return _side[key]
 
 
