@@ -866,9 +866,16 @@ int adalog_gen_uniform_cand(const float* x, int64_t U, int K, int64_t ldx, const
   const int npg = 256 / tpc;                             // candidate groups per CTA
   dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
   cudaStream_t st = (cudaStream_t)stream;
+  // max-shared carve-out like the GEMM kernel: CTAs of kernels that want different L1/shared splits do not share an SM,
+  // and the generator of chunk i+1 is meant to run in the registers the GEMM of chunk i leaves free
 #define ADALOG_LAUNCH_UCAND(KR, RS, I8)                                                                              \
-  gen_uniform_cand_kernel<KR, RS, I8><<<grid, tpc * npg, 0, st>>>(x, K, ldx, cs, cz, P, pstride, gstride, g_div,     \
-                                                                   g_mod, u_base, n_levels, out, kpad, rowsum, tpc)
+  do {                                                                                                               \
+    cudaFuncSetAttribute(gen_uniform_cand_kernel<KR, RS, I8>, cudaFuncAttributePreferredSharedMemoryCarveout,       \
+                         cudaSharedmemCarveoutMaxShared);                                                            \
+    gen_uniform_cand_kernel<KR, RS, I8><<<grid, tpc * npg, 0, st>>>(x, K, ldx, cs, cz, P, pstride, gstride, g_div,   \
+                                                                     g_mod, u_base, n_levels, out, kpad, rowsum,     \
+                                                                     tpc);                                           \
+  } while (0)
   if (dtype == ADALOG_I8) ADALOG_LAUNCH_UCAND(1, false, true);
   else if (krep == 1) { if (rowsum) ADALOG_LAUNCH_UCAND(1, true, false); else ADALOG_LAUNCH_UCAND(1, false, false); }
   else                { if (rowsum) ADALOG_LAUNCH_UCAND(3, true, false); else ADALOG_LAUNCH_UCAND(3, false, false); }
@@ -887,6 +894,10 @@ int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const flo
   cudaStream_t st = (cudaStream_t)stream;
   ADALOG_REQUIRE(2 * n_levels <= 64, -2, "gen_log_cand: AdaLog sweeps support n_bits <= 6 (bf16-exact numerators)");
   const size_t lut_bytes = (size_t)(ADALOG_P / grid.y) * (2 * n_levels + 1) * sizeof(float);
+  cudaFuncSetAttribute(gen_log_cand_lut_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(gen_log_cand_lut_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
   if (cs)
     gen_log_cand_lut_kernel<true><<<grid, tpc * npg, lut_bytes, st>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
                                                                       out, kpad, tpc, 0x2D000000u);

@@ -34,6 +34,11 @@ sc = torch.linspace(2.0, 4.0, 128, device=DEV).view(1, -1)
 which = sys.argv[1] if len(sys.argv) > 1 else 'a'
 if which == 'a':
     e = sweep.linear_err_log(ctx, W.view(1, Do, D), b, wq, lq, sc, qc)
+elif which == 'u':      # uniform int8 activation sweep of the same shape
+    x0 = torch.randn(Bn, T, D, device=DEV)
+    uctx = sweep.LinearCtx(x0, torch.nn.functional.linear(x0, W, b), Do)
+    acs, acz = O.activation_candidates(x0, 8, 128, False)
+    e = sweep.linear_err_a(uctx, W.view(1, Do, D), b, wq, acs, acz, 8)
 else:
     e = sweep.linear_err_w(ctx, W.view(1, Do, D), b, lq, cs, cz, 8)
 torch.cuda.synchronize()
