@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace adalog {
 
@@ -33,9 +34,17 @@ constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;   // 320
 
 // barriers and the epilogue's per-tile y / column-scale staging live in STATIC shared memory so that the compiler
 // keeps the shared address space (LDS/STS, not generic LD/ST); the operand ring is dynamic (1024-byte aligned).
+constexpr int kCsCols = 1024;           // MODE_CS: most columns (N tiles per split x BN) one CTA may cover
+constexpr int kSlabsPerGroup = (kMaxBN / 32 + kEpiGroups - 1) / kEpiGroups;   // 32-column slabs one epilogue warp handles per tile
 struct __align__(16) SmemTail {
-  float ysm[2][kMaxBN];       // 16-byte aligned: read back as float4 broadcasts
-  float csm[2][kMaxBN];
+  // per-WARP staging of y - cb and cs for the warp's own slabs (16-byte aligned: read back as float4 broadcasts).
+  // Private to the warp, so a tile needs two __syncwarp()s and no CTA-wide barrier: the eight epilogue warps drift
+  // apart and fill each other's TMEM-load and barrier latencies.
+  float ysw[kEpiWarps][kSlabsPerGroup * 32];
+  // MODE_CS: column scale / bias of ALL the CTA's N tiles, staged once per CTA (they do not depend on the unit);
+  // zero beyond the CTA's columns so ragged / padded columns read 0
+  float cs_all[kCsCols + kMaxBN];
+  float cb_all[kCsCols + kMaxBN];
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t tfull[kAccStages];
@@ -166,7 +175,9 @@ struct KArgs {
 enum { MODE_CS = 0, MODE_RB = 1, MODE_PLAIN = 2, MODE_NOEPI = 3 /* diagnostic: pipeline only, no epilogue math */ };
 
 template <int MODE, bool DEBUG, bool I8>
-__global__ void __launch_bounds__(kThreads, 1)
+// 152 registers x 320 threads leave 16.9k registers of the SM free: one 256-thread generator CTA (64 registers) of the
+// next chunk runs beside this kernel's single CTA
+__global__ void __maxnreg__(152)
 cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -265,55 +276,70 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int ew = warp - kEpiWarp0;
     const int eg = ew >> 2;                                 // column group 0..kEpiGroups-1
     const int et = ((warp & 3) << 5) | lane;                // 0..127 = candidate p = TMEM lane (a warp reaches lanes 32*(warp%4)..)
-    const int st = threadIdx.x - kEpiWarp0 * 32;            // 0..kEpiThreads-1: staging slot (one y column each)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr int G = kEpiGroups;
+    float* const ysw = tail_s.ysw[ew];
     double acc64 = 0.0;
     float rs = 0.0f, rb = 0.0f;
     long long cur_ri = -1;
-    float yreg = 0.0f, breg = 0.0f, creg = 0.0f;
-    // global loads for tile t+1 are issued before tile t's math and only consumed (y - cb, store to smem) at the
-    // top of the next iteration, so their latency hides under the epilogue arithmetic
-    auto prefetch = [&](int u, int n0) {
-      const int n = n0 + st;
-      float yv = 0.0f, bv = 0.0f, cv = 0.0f;
-      if (st < kMaxBN && st < a.BN && n < a.N) {
-        yv = __ldg(a.y + (long long)u * a.ldy + n);
-        if (HAS_CS) { bv = __ldg(a.cb + n); cv = __ldg(a.cs + n); }
+    float yreg[kSlabsPerGroup];
+#pragma unroll
+    for (int i = 0; i < kSlabsPerGroup; ++i) yreg[i] = 0.0f;
+    if (HAS_CS) {
+      const int st = threadIdx.x - kEpiWarp0 * 32;
+      const int ncs = n_nt * a.BN;                       // <= kCsCols (validated on the host)
+      for (int idx = st; idx < kCsCols + kMaxBN; idx += kEpiThreads) {
+        float cv = 0.0f, bv = 0.0f;
+        if (idx < ncs) {
+          const int ti = idx / a.BN;
+          const int c = idx - ti * a.BN;
+          const int n = (nt0 + ti) * a.BN + c;
+          if (n < a.N) { cv = __ldg(a.cs + n); bv = __ldg(a.cb + n); }
+        }
+        tail_s.cs_all[idx] = cv;
+        tail_s.cb_all[idx] = bv;
       }
-      yreg = yv; breg = bv; creg = cv;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    }
+    // global loads of y for tile t+1 (lane l: column l of each of the warp's slabs) are issued before tile t's math and
+    // only consumed (y - cb, store to the warp's staging row) at the top of the next iteration, so their latency hides
+    // under the epilogue arithmetic.  Columns beyond the tile / beyond N stage as 0.
+    auto prefetch = [&](int u, int n0) {
+#pragma unroll
+      for (int i = 0; i < kSlabsPerGroup; ++i) {
+        const int c = (eg + i * G) * 32 + lane;
+        const int n = n0 + c;
+        yreg[i] = (c < a.BN && n < a.N) ? __ldg(a.y + (long long)u * a.ldy + n) : 0.0f;
+      }
     };
     // four independent accumulators (same instruction sequence for every lane = candidate, so equal candidates still
     // produce bit-equal sums)
     float acc4[4];
     // accumulator word -> FP32: kind::f16 accumulates in FP32, kind::i8 in S32 (exact integer dot products)
     auto accf = [](uint32_t w) -> float { return I8 ? __int2float_rn((int)w) : __uint_as_float(w); };
-    auto quad = [&](const uint32_t (&d)[32], int j, int c0, int buf, float rs, float rb) {
-      const float4 yv = *reinterpret_cast<const float4*>(&tail_s.ysm[buf][c0 + j]);
+    // four columns j..j+3 of a slab staged at local offset l0; MASKED: columns >= lim contribute nothing
+    auto quad = [&](auto masked, const uint32_t (&d)[32], int j, int l0, int cc, int lim, float rs, float rb) {
+      constexpr bool MASKED = decltype(masked)::value;
+      const float4 yv = *reinterpret_cast<const float4*>(&ysw[l0 + j]);
       const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+      float c4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
       if (HAS_CS) {
-        const float4 cv = *reinterpret_cast<const float4*>(&tail_s.csm[buf][c0 + j]);
-        const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
+        const float4 cv = *reinterpret_cast<const float4*>(&tail_s.cs_all[cc + j]);
+        c4[0] = cv.x; c4[1] = cv.y; c4[2] = cv.z; c4[3] = cv.w;
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float diff = fmaf(-rs, accf(d[j + e]) * c4[e], y4[e]);
-          acc4[e] = fmaf(diff, diff, acc4[e]);
-        }
-      } else if (MODE == MODE_RB) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float diff = y4[e] - fmaf(rs, accf(d[j + e]), rb);
-          acc4[e] = fmaf(diff, diff, acc4[e]);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float diff = fmaf(-rs, accf(d[j + e]), y4[e]);
-          acc4[e] = fmaf(diff, diff, acc4[e]);
-        }
+      for (int e = 0; e < 4; ++e) {
+        float diff;
+        if (HAS_CS) diff = fmaf(-rs, accf(d[j + e]) * c4[e], y4[e]);
+        else if (MODE == MODE_RB) diff = y4[e] - fmaf(rs, accf(d[j + e]), rb);
+        else diff = fmaf(-rs, accf(d[j + e]), y4[e]);
+        if (MASKED) diff = (j + e < lim) ? diff : 0.0f;
+        acc4[e] = fmaf(diff, diff, acc4[e]);
       }
     };
-    // one 32-column slab of the accumulator
-    auto consume = [&](const uint32_t (&d)[32], int c0, int lim, int buf, float rs, float rb, int n0, int ncols) {
+    // one 32-column slab of the accumulator (tile column c0, y staged at local offset l0, column scales at cs_all[cc],
+    // lim valid columns)
+    auto consume = [&](const uint32_t (&d)[32], int c0, int l0, int cc, int lim, float rs, float rb, int n0, int ncols) {
       if (DEBUG) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -321,24 +347,14 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if (MODE == MODE_NOEPI) {
         acc4[0] += __uint_as_float(d[0]);
-      } else if (lim == 32) {
+      } else if (lim >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) quad(d, j, c0, buf, rs, rb);
+        for (int j = 0; j < 32; j += 4) quad(std::false_type{}, d, j, l0, cc, 32, rs, rb);
       } else {
-        // ragged last slab: whole quads first, then at most three single columns
-        const int lim4 = lim & ~3;
+        // ragged last slab: whole quads up to the one that holds column lim-1, its excess columns masked
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          if (j < lim4) quad(d, j, c0, buf, rs, rb);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j >= lim4 && j < lim) {
-            float dv = accf(d[j]);
-            if (HAS_CS) dv *= tail_s.csm[buf][c0 + j];
-            const float diff = tail_s.ysm[buf][c0 + j] - fmaf(rs, dv, rb);
-            acc4[j & 3] = fmaf(diff, diff, acc4[j & 3]);
-          }
-        }
+          if (j < lim) quad(std::true_type{}, d, j, l0, cc, lim, rs, rb);
       }
     };
     // incremental work-list position (no per-tile integer division)
@@ -352,6 +368,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int t = 0; t < n_tiles; ++t) {
       const int n0 = (nt0 + cnt) * a.BN;
+      const int toff = cnt * a.BN;               // this tile's columns inside cs_all / cb_all
       const int ncols = min(a.BN, a.N - n0);
       const long long ri_t = ri;
       // advance to tile t+1
@@ -360,12 +377,11 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (++rrem == a.rs_div) { rrem = 0; if (++ri == a.rs_mod) ri = 0; }
       }
       const uint32_t as = t & 1, aphase = (t >> 1) & 1;
-      const int buf = t & 1;
-      if (st < kMaxBN) {
-        tail_s.ysm[buf][st] = yreg - breg;
-        if (HAS_CS) tail_s.csm[buf][st] = creg;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      __syncwarp();                      // every lane is done reading the previous tile's staging row
+#pragma unroll
+      for (int i = 0; i < kSlabsPerGroup; ++i)
+        ysw[i * 32 + lane] = HAS_CS ? yreg[i] - tail_s.cb_all[toff + (eg + i * G) * 32 + lane] : yreg[i];
+      __syncwarp();
       if (t + 1 < n_tiles) prefetch(cu, (nt0 + cnt) * a.BN);
       if (ri_t != cur_ri) {
         cur_ri = ri_t;
@@ -379,17 +395,17 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // this group's slabs eg, eg+G, eg+2G, ...; TMEM -> registers double buffered: the load of the next slab is in
       // flight while the current one is reduced
       const int nslab = (ncols + 31) >> 5;
-      constexpr int G = kEpiGroups;
       uint32_t da[32], db[32];
       if (eg < nslab) tmem_ld32(tbase + eg * 32, da);
-      for (int sl = eg; sl < nslab; sl += 2 * G) {
+      int l0 = 0;
+      for (int sl = eg; sl < nslab; sl += 2 * G, l0 += 64) {
         tmem_ld_wait();
         if (sl + G < nslab) tmem_ld32(tbase + (sl + G) * 32, db);
-        consume(da, sl * 32, min(32, ncols - sl * 32), buf, rs, rb, n0, ncols);
+        consume(da, sl * 32, l0, toff + sl * 32, ncols - sl * 32, rs, rb, n0, ncols);
         if (sl + G < nslab) {
           tmem_ld_wait();
           if (sl + 2 * G < nslab) tmem_ld32(tbase + (sl + 2 * G) * 32, da);
-          consume(db, (sl + G) * 32, min(32, ncols - (sl + G) * 32), buf, rs, rb, n0, ncols);
+          consume(db, (sl + G) * 32, l0 + 32, toff + (sl + G) * 32, ncols - (sl + G) * 32, rs, rb, n0, ncols);
         }
       }
       acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
@@ -462,6 +478,8 @@ static int validate(const adalog_gemm_err_args* a, bool need_partial) {
   ADALOG_REQUIRE(a->y && (a->partial || !need_partial), -1, "cand_gemm_err: y / partial required");
   const int NT = (a->N + a->BN - 1) / a->BN;
   ADALOG_REQUIRE(a->S <= NT, -1, "cand_gemm_err: more N splits than N tiles");
+  ADALOG_REQUIRE(!a->cs || ((NT + a->S - 1) / a->S) * a->BN <= kCsCols, -1,
+                 "cand_gemm_err: with column scales a CTA covers at most 1024 columns (raise S)");
   return 0;
 }
 

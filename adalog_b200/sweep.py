@@ -76,7 +76,7 @@ CTA_FIXED_COST = 8000        # prologue + pipeline fill + epilogue drain of one 
 
 
 @functools.lru_cache(maxsize=4096)
-def _launch_plan(nu, ug, NT, b_bytes_per_group=0, unit_bytes=0, tile_cost=16384):
+def _launch_plan(nu, ug, NT, b_bytes_per_group=0, unit_bytes=0, tile_cost=16384, max_tps=1 << 30):
     """static CTA partition of one launch: (groups, units per CTA, CTAs per group, N-tile splits, split_fast).
 
     L2 residency.  A CTA re-reads its unit's 128 candidate rows (unit_bytes) once per N tile, and all CTAs walk the
@@ -90,9 +90,10 @@ def _launch_plan(nu, ug, NT, b_bytes_per_group=0, unit_bytes=0, tile_cost=16384)
 
     Wave quantisation.  All CTAs of a launch do equal work, so the launch takes ceil(CTAs / 148) rounds of the
     largest CTA; among the partitions the L2 rules allow, the one minimising rounds x (tiles per CTA x tile_cost +
-    fixed CTA cost) is taken (tile_cost in SM clocks: the larger of the tile's MMA time and its 8 x BN TMEM read-out)."""
+    fixed CTA cost) is taken (tile_cost in SM clocks: the larger of the tile's MMA time and its 8 x BN TMEM read-out).
+    max_tps: most N tiles one CTA may cover (the kernel stages column scales for at most 1024 columns per CTA)."""
     groups = nu // ug
-    s_min, split_fast = min(NT, max(1, math.ceil(b_bytes_per_group / L2_SLICE_BYTES))), False
+    s_min, split_fast = min(NT, max(1, math.ceil(b_bytes_per_group / L2_SLICE_BYTES), math.ceil(NT / max_tps))), False
     if NT > 1 and unit_bytes * min(NUM_SMS, nu) > L2_CAND_BYTES:
         split_fast = True
         s_min = min(NT, max(s_min, math.ceil(unit_bytes * NUM_SMS / L2_CAND_TARGET)))
@@ -141,7 +142,8 @@ def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=
     def gemm(u0, nu, buf):
         ug = nu if single else UG
         groups, upc, cpg, S, sf = _launch_plan(nu, ug, NT, N * ka * (1 if i8 else 2), unit_elems,
-                                               max((ka // 64) * BN * (1 if i8 else 2), 8 * BN))
+                                               max((ka // 64) * BN * (1 if i8 else 2), 8 * BN),
+                                               (1024 // BN) if cs is not None else 1 << 30)
         part = ops.cand_gemm_err(buf, nu * ops.P_TILE, Bm, ka, N, nu, ug, brpg, 0 if single else u0 // UG, u0, y,
                                  u0 * ldy, ldy, rs, rb, rs_div, rs_mod, cs, cb, upc, S, BN, k_true, i8, sf)
         return part.view(S, groups, cpg, ops.P_TILE).sum(dim=(0, 2))
