@@ -30,6 +30,23 @@ class GemmErrArgs(ctypes.Structure):
     ]
 
 
+class FusedArgs(ctypes.Structure):
+    """mirror of adalog_fused_args"""
+    _fields_ = [
+        ('x', c_vp), ('ldx', c_i64), ('Bm', c_vp), ('b_rows', c_i64),
+        ('K', ctypes.c_int32), ('KB', ctypes.c_int32), ('N', ctypes.c_int32), ('BN', ctypes.c_int32),
+        ('U', ctypes.c_int32), ('UG', ctypes.c_int32), ('upc', ctypes.c_int32),
+        ('P', ctypes.c_int32), ('n_levels', ctypes.c_int32),
+        ('gen', ctypes.c_int32), ('dtype', ctypes.c_int32), ('epi_warps', ctypes.c_int32),
+        ('brpg', c_i64), ('g_base', c_i64), ('u_base', c_i64),
+        ('cs', c_vp), ('cz', c_vp), ('pstride', c_i64), ('gstride', c_i64), ('g_div', c_i64), ('g_mod', c_i64),
+        ('cq', c_vp), ('mtab', c_vp),
+        ('y', c_vp), ('ldy', c_i64),
+        ('rs', c_vp), ('rs_div', c_i64), ('rs_mod', c_i64),
+        ('partial', c_vp),
+    ]
+
+
 # name -> argtypes; every function returns int except adalog_last_error
 SIGNATURES = {
     'adalog_version': [],
@@ -46,13 +63,15 @@ SIGNATURES = {
     'adalog_gen_split3': [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_vp],
     'adalog_cand_gemm_err_grid': [ctypes.POINTER(GemmErrArgs)],
     'adalog_cand_gemm_err': [ctypes.POINTER(GemmErrArgs), c_vp],
+    'adalog_fused_cand_gemm_err_grid': [ctypes.POINTER(FusedArgs)],
+    'adalog_fused_cand_gemm_err': [ctypes.POINTER(FusedArgs), c_vp],
     'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
 }
 
 _lib = None
 # kernels launched through this binding (bench.py reports it as gpu_launches)
 LAUNCHES = {'count': 0}
-_NO_LAUNCH = {'adalog_version', 'adalog_cand_gemm_err_grid'}
+_NO_LAUNCH = {'adalog_version', 'adalog_cand_gemm_err_grid', 'adalog_fused_cand_gemm_err_grid'}
 
 
 class AdalogError(RuntimeError):

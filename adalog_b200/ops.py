@@ -9,19 +9,20 @@ import math
 import torch
 
 from . import _lib
-from ._lib import AdalogError, GemmErrArgs, call
+from ._lib import AdalogError, FusedArgs, GemmErrArgs, call
 
 P_TILE = 128   # ADALOG_P
 BK = 64        # ADALOG_BK
 
 # bench.py sets PROFILE['on']: every candidate-GEMM launch is then bracketed by CUDA events on its stream and its
 # algorithmic FLOPs recorded, which is how roofline.achieved is measured live inside the timed region
-PROFILE = {'on': False, 'gemm': []}
+PROFILE = {'on': False, 'gemm': [], 'fused': []}
 
 
 def profile_reset(on):
     PROFILE['on'] = bool(on)
     PROFILE['gemm'] = []
+    PROFILE['fused'] = []
 
 
 def profile_gemm_summary():
@@ -262,6 +263,70 @@ def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, l
     else:
         call('adalog_cand_gemm_err', ctypes.byref(a), _stream())
     return partial
+
+
+SMEM_LIMIT = 227 * 1024 - 9600   # dynamic shared memory the fused kernel may ask for (its static part is ~9 KB)
+
+
+def fused_plan(K, N, i8, log, n_levels):
+    """(KB, BN) when the fused generator + GEMM kernel can take the shape (one N tile, K <= 4 blocks, operands fit in
+    shared memory), else None (the caller then uses the generator -> workspace -> GEMM path)."""
+    el = 2 * BK if i8 else BK
+    KB = (K + el - 1) // el
+    if N > 256 or KB > 4:
+        return None
+    BN = pick_bn(N)
+    smem = 1024 + KB * 16384 + KB * BN * 128 + (P_TILE * (2 * n_levels + 1) * 4 if log else 0)
+    if smem > SMEM_LIMIT or (log and (i8 or 2 * n_levels > 64)):
+        return None
+    return KB, BN
+
+
+def fused_cand_gemm_err(x2d, K, Bm, N, U, UG, brpg, y, ldy, rs, rs_div, rs_mod, upc, n_levels, P, cs=None, cz=None,
+                        pstride=0, gstride=0, g_div=1, g_mod=1, cq=None, mtab=None, i8=False):
+    """One launch of adalog_fused_cand_gemm_err over all U units.  Returns FP64 partial [grid, 128]."""
+    log = cq is not None
+    KB, BN = fused_plan(K, N, i8, log, n_levels)
+    _cuda(x2d, Bm, y, rs)
+    assert x2d.dtype == torch.float32 and x2d.stride(1) == 1
+    a = FusedArgs()
+    a.x, a.ldx = x2d.data_ptr(), int(x2d.stride(0))
+    a.Bm, a.b_rows = Bm.data_ptr(), int(Bm.shape[0])
+    a.K, a.KB, a.N, a.BN = int(K), int(KB), int(N), int(BN)
+    a.U, a.UG, a.upc, a.P, a.n_levels = int(U), int(UG), int(upc), int(P), int(n_levels)
+    a.gen, a.dtype = (1 if log else 0), (I8 if i8 else BF16)
+    # 14 worker warps: E reduce the error (~20 warp-instructions per column and unit), 14 - E generate candidates
+    # (~36 per K element for a uniform quantizer, ~64 for AdaLog); take the better balanced of E = 4 / 8
+    ck = (64 if log else 36) * K
+    a.epi_warps = min((4, 8), key=lambda e: max(20.0 * N / e, ck / (14 - e)))
+    a.brpg, a.g_base, a.u_base = int(brpg), 0, 0
+    if log:
+        a.cq, a.mtab = cq.data_ptr(), mtab.data_ptr()
+    else:
+        a.cs, a.cz = cs.data_ptr(), cz.data_ptr()
+        a.pstride, a.gstride = int(pstride), int(gstride)
+    a.g_div, a.g_mod = int(g_div), int(g_mod)
+    a.y, a.ldy = y.data_ptr(), int(ldy)
+    a.rs, a.rs_div, a.rs_mod = rs.data_ptr(), int(rs_div), int(rs_mod)
+    grid = call('adalog_fused_cand_gemm_err_grid', ctypes.byref(a))
+    partial = torch.empty(grid, P_TILE, dtype=torch.float64, device=Bm.device)
+    a.partial = partial.data_ptr()
+    if PROFILE['on']:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call('adalog_fused_cand_gemm_err', ctypes.byref(a), _stream())
+        e1.record()
+        PROFILE['fused'].append((e0, e1, 2.0 * P_TILE * U * N * K))
+    else:
+        call('adalog_fused_cand_gemm_err', ctypes.byref(a), _stream())
+    return partial
+
+
+def profile_fused_summary():
+    """(flops, milliseconds, launches) of the fused generator + GEMM launches recorded since profile_reset(True)"""
+    torch.cuda.synchronize()
+    return (sum(f for _, _, f in PROFILE['fused']), sum(e0.elapsed_time(e1) for e0, e1, _ in PROFILE['fused']),
+            len(PROFILE['fused']))
 
 
 def debug_gemm_tile(A, Bm):

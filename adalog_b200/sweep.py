@@ -395,6 +395,40 @@ def _matmul_reduce(res, ctx, P, head_channel_wise, pool_heads, n_cols_total):
     return (-(tot[:P] / (n_cols_total * ctx.H))).float()                    # [P]
 
 
+FUSED = os.environ.get('ADALOG_B200_FUSED', '1') == '1'
+
+
+@functools.lru_cache(maxsize=1024)
+def _fused_upc(groups, ug, K, N):
+    """units per CTA of the fused kernel: a CTA stays inside one group (it loads the group's fixed operand once), all
+    CTAs do equal work, so the launch takes ceil(CTAs / 148) rounds of the largest CTA."""
+    unit_cost = 10 * K + 10 * N            # worker-warp clocks per unit: generation ~ K, error arithmetic ~ N
+    best = None
+    for cpg in range(1, min(ug, 16) + 1):
+        upc = math.ceil(ug / cpg)
+        ctas = groups * math.ceil(ug / upc)
+        cost = math.ceil(ctas / NUM_SMS) * (upc * unit_cost + CTA_FIXED_COST)
+        if best is None or cost < best[0]:
+            best = (cost, upc)
+    return best[1]
+
+
+def _use_fused(K, N, i8, log, n_levels):
+    """The fused generator + GEMM kernel is taken where it measured faster than generator -> workspace -> GEMM
+    (DeiT-S, 128 images: QK^T sweeps 1.95 vs 2.44 ms, P.V base search 5.3 vs 5.8 ms); for a uniform candidate side with
+    a long reduction (P.V value sweep, K = 197) its 14 worker warps are short of issue slots (2.3 vs 1.9 ms)."""
+    if not FUSED or ops.fused_plan(K, N, i8, log, n_levels) is None:
+        return False
+    return log or K <= 128
+
+
+def _run_fused(x2d, K, Bm, N, U, UG, y, ldy, rs, H, n_levels, P, i8=False, **cand):
+    """all units of an attention sweep in ONE launch of the fused generator + GEMM kernel -> [U/UG, 128] FP64"""
+    upc = _fused_upc(U // UG, UG, K, N)
+    part = ops.fused_cand_gemm_err(x2d, K, Bm, N, U, UG, N, y, ldy, rs, UG, H, upc, n_levels, P, i8=i8, **cand)
+    return part.view(U // UG, -1, ops.P_TILE).sum(dim=1)
+
+
 def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, head_channel_wise):
     """matmul.py:135-163: candidates on A, fixed quantised B -> [P, H] (or [P])."""
     P = cs.shape[0]
@@ -402,7 +436,9 @@ def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, head_channel_wise):
     c2, z2 = _cand2d(cs, cz)                                     # [P, H] or [P, 1]
     gs = 1 if c2.shape[1] == H else 0
     sB, zB = _head_params(Bq, H)
-    Bm, _ = ops.gen_uniform_fixed(ctx.Bt2d, sB, zB, ctx.S2, H, Bq.n_levels)
+    i8 = False       # bf16 operands: at K = 64 an int8 row is as long, and the fused int8 producer measured slower
+    fused = _use_fused(ctx.Kd, ctx.S2, i8, False, n_levels_A)
+    Bm, _ = ops.gen_uniform_fixed(ctx.Bt2d, sB, zB, ctx.S2, H, Bq.n_levels, i8=i8)
     ka = ops.kpad(ctx.Kd)
 
     def gen(u0, nu, out):
@@ -411,12 +447,17 @@ def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, head_channel_wise):
     cfull = c2 if gs else c2.expand(P, H)
     rs = (_pad128(cfull.t().contiguous()).double() * sB.double().reshape(H, 1)).float().contiguous()   # [H,128]
     U = ctx.Bn * H * ctx.S1
-    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H, k_true=ctx.Kd)
+    if fused:
+        res = _run_fused(ctx.A2d, ctx.Kd, Bm, ctx.S2, U, ctx.S1, ctx.y2d, ctx.S2, rs, H, n_levels_A, P, i8=i8,
+                         cs=c2, cz=z2, pstride=c2.shape[1], gstride=gs, g_div=ctx.S1, g_mod=H)
+    else:
+        res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H,
+                            k_true=ctx.Kd)
     return _matmul_reduce(res, ctx, P, head_channel_wise, False, ctx.S1 * ctx.S2)
 
 
-def _fixed_A_operand(ctx, Aq):
-    """quant_input_A(A) as a bf16 operand, rows (b,h,s1); returns (Bm, per-head scale FP64 [H])."""
+def _fixed_A_operand(ctx, Aq, i8=False):
+    """quant_input_A(A) as a bf16 (or int8) operand, rows (b,h,s1); returns (Bm, per-head scale FP64 [H])."""
     H = ctx.H
     if getattr(Aq, 'is_log', False):
         if not hasattr(Aq, 'table2'):
@@ -427,7 +468,7 @@ def _fixed_A_operand(ctx, Aq):
         Bm = ops.gen_log_fixed(ctx.A2d, Aq.scale, Aq.q, None, Aq.table1, m2, nl)
         return Bm, (_f32(Aq.scale).double().reshape(1) / (4 * nl - 2)).expand(H)
     sA, zA = _head_params(Aq, H)
-    Bm, _ = ops.gen_uniform_fixed(ctx.A2d, sA, zA, ctx.S1, H, Aq.n_levels)
+    Bm, _ = ops.gen_uniform_fixed(ctx.A2d, sA, zA, ctx.S1, H, Aq.n_levels, i8=i8)
     return Bm, sA.double()
 
 
@@ -437,7 +478,9 @@ def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, head_channel_wise):
     H = ctx.H
     c2, z2 = _cand2d(cs, cz)
     gs = 1 if c2.shape[1] == H else 0
-    Bm, sA = _fixed_A_operand(ctx, Aq)
+    i8 = False
+    fused = _use_fused(ctx.Kd, ctx.S1, i8, False, n_levels_B)
+    Bm, sA = _fixed_A_operand(ctx, Aq, i8)
     ka = ops.kpad(ctx.Kd)
 
     def gen(u0, nu, out):
@@ -446,7 +489,12 @@ def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, head_channel_wise):
     cfull = c2 if gs else c2.expand(P, H)
     rs = (_pad128(cfull.t().contiguous()).double() * sA.reshape(H, 1)).float().contiguous()
     U = ctx.Bn * H * ctx.S2
-    res = run_cand_gemm(gen, U, ka, ctx.S2, Bm, ctx.S1, ctx.S1, ctx.yT2d, ctx.S1, rs, None, ctx.S2, H, k_true=ctx.Kd)
+    if fused:
+        res = _run_fused(ctx.Bt2d, ctx.Kd, Bm, ctx.S1, U, ctx.S2, ctx.yT2d, ctx.S1, rs, H, n_levels_B, P, i8=i8,
+                         cs=c2, cz=z2, pstride=c2.shape[1], gstride=gs, g_div=ctx.S2, g_mod=H)
+    else:
+        res = run_cand_gemm(gen, U, ka, ctx.S2, Bm, ctx.S1, ctx.S1, ctx.yT2d, ctx.S1, rs, None, ctx.S2, H,
+                            k_true=ctx.Kd)
     return _matmul_reduce(res, ctx, P, head_channel_wise, False, ctx.S1 * ctx.S2)
 
 
@@ -466,7 +514,12 @@ def matmul_err_A_log_base(ctx, Bq, cq, n_levels_A):
 
     rs = (sB.double().reshape(H, 1) / (4 * n_levels_A - 2)).expand(H, ops.P_TILE).float().contiguous()
     U = ctx.Bn * H * ctx.S1
-    res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H, k_true=ctx.Kd)
+    if _use_fused(ctx.Kd, ctx.S2, False, True, n_levels_A):
+        res = _run_fused(ctx.A2d, ctx.Kd, Bm, ctx.S2, U, ctx.S1, ctx.y2d, ctx.S2, rs, H, n_levels_A, P,
+                         cq=q1, mtab=mtab, g_div=ctx.S1, g_mod=H)
+    else:
+        res = run_cand_gemm(gen, U, ka, ctx.S1, Bm, ctx.S2, ctx.S2, ctx.y2d, ctx.S2, rs, None, ctx.S1, H,
+                            k_true=ctx.Kd)
     return _matmul_reduce(res, ctx, P, True, True, ctx.S1 * ctx.S2).reshape(P, 1)
 
 

@@ -145,6 +145,44 @@ typedef struct {
 int adalog_cand_gemm_err_grid(const adalog_gemm_err_args* a);
 int adalog_cand_gemm_err(const adalog_gemm_err_args* a, void* stream);
 
+/* ---------------------------------------------------------------- fused generator + GEMM + error (attention matmuls)
+ * replaces: quant_layers/matmul.py:135-163 (_search_best_A_scale), :173-201 (_search_best_B_scale), :321-351
+ * (post-softmax AdaLog base search).  Same arithmetic and same result layout as adalog_gen_*_cand followed by
+ * adalog_cand_gemm_err, for the shapes of the attention products (one N tile, K <= 256 bf16 / 512 int8), but the
+ * 128x-expanded candidate operand is generated inside the GEMM kernel, straight into shared memory, and never
+ * touches HBM; the group's fixed operand is loaded once per CTA.
+ *
+ * x  [U, K] FP32 (row pitch ldx): source rows of the candidate side, unit u = row u.
+ * Bm [G*brpg, KB*64|128]: fixed operand as written by adalog_gen_uniform_fixed / adalog_gen_log_fixed.
+ * gen = ADALOG_GEN_UNIFORM: candidate p of unit u uses cs/cz[p*pstride + ((u_base+u)/g_div % g_mod)*gstride];
+ * gen = ADALOG_GEN_LOG: unscaled AdaLog code rint(-log2(x)*37/cq[p]) (the post-softmax form), value from mtab.
+ * yhat = rs[ri*128+p] * D, ri = (u_base+u)/rs_div % rs_mod;  partial[x*128 + p] (FP64), x < grid.
+ * g_div, rs_div and u_base must be multiples of UG (a CTA works inside one group). */
+#define ADALOG_GEN_UNIFORM 0
+#define ADALOG_GEN_LOG 1
+typedef struct {
+  const float* x;     int64_t ldx;
+  const void* Bm;     int64_t b_rows;
+  int32_t K;          /* true reduction length */
+  int32_t KB;         /* ceil(K / 64) (bf16) or ceil(K / 128) (int8), <= 4 */
+  int32_t N;          /* valid columns per group, <= BN */
+  int32_t BN;         /* tile width, multiple of 16, <= 256 */
+  int32_t U;          int32_t UG;          int32_t upc;
+  int32_t P;          int32_t n_levels;    /* of the candidate-side quantizer */
+  int32_t gen;        int32_t dtype;
+  int32_t epi_warps;  /* 4 or 8 of the kernel's 14 worker warps reduce the error, the others generate candidates */
+  int64_t brpg;       int64_t g_base;      int64_t u_base;
+  const float* cs;    const float* cz;     int64_t pstride; int64_t gstride; int64_t g_div; int64_t g_mod;
+  const long long* cq; const float* mtab;
+  const float* y;     int64_t ldy;
+  const float* rs;    int64_t rs_div;      int64_t rs_mod;
+  double* partial;    /* [grid * 128] */
+} adalog_fused_args;
+
+/* returns the grid size (so the caller can size `partial`), or negative (e.g. -3: does not fit in shared memory) */
+int adalog_fused_cand_gemm_err_grid(const adalog_fused_args* a);
+int adalog_fused_cand_gemm_err(const adalog_fused_args* a, void* stream);
+
 /* plain (non-candidate) debug GEMM through the same tcgen05 pipeline: D[m,n] FP32 for A [128,ka], Bm [N,ka];
  * used by the tests to validate descriptors / swizzle / TMEM addressing in isolation. */
 int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, int dtype, void* stream);

@@ -139,9 +139,14 @@ def perf_matmul():
         ops.profile_reset(True)
         t = timed(fn, 2)
         flops, ms, n = ops.profile_gemm_summary()
+        ff, fms, fn_ = ops.profile_fused_summary()
         ops.profile_reset(False)
-        print(f'{tag}: {t:.2f} ms per sweep; GEMM kernel {ms / 3:.2f} ms in {n // 3} launches '
-              f'({flops / ms / 1e9:.0f} TFLOP/s); generator+rest {t - ms / 3:.2f} ms')
+        if fn_:
+            print(f'{tag}: {t:.2f} ms per sweep; FUSED kernel {fms / 3:.2f} ms in {fn_ // 3} launches '
+                  f'({ff / fms / 1e9:.0f} TFLOP/s); rest {t - fms / 3:.2f} ms')
+        else:
+            print(f'{tag}: {t:.2f} ms per sweep; GEMM kernel {ms / 3:.2f} ms in {n // 3} launches '
+                  f'({flops / ms / 1e9:.0f} TFLOP/s); generator+rest {t - ms / 3:.2f} ms')
 
 
 def _logq():
