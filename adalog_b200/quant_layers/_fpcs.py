@@ -77,6 +77,15 @@ def chunked_quantile(x2, pct):
     while x2.numel() // (g * mbs) > (1 << 24):
         mbs *= 2
     x2 = x2.reshape(g, mbs, -1)
-    up = torch.quantile(x2, pct.to(x2.device), dim=-1).mean(dim=-1)
-    lo = torch.quantile(x2, (1 - pct).to(x2.device), dim=-1).mean(dim=-1)
-    return up, lo        # each [2, g]
+    up, lo = quantile_pair(x2, pct, -1)
+    return up.mean(dim=-1), lo.mean(dim=-1)        # each [2, g]
+
+
+def quantile_pair(x, pct, dim):
+    """(quantile(x, pct), quantile(x, 1 - pct)) along dim with ONE sort: torch.quantile sorts once per call and
+    interpolates every requested q independently, so the values are bit-identical to the reference's two calls
+    (linear.py:441-442, :459-471; matmul.py:223-230; conv.py:280-281)."""
+    n = pct.numel()
+    q = torch.cat([pct, 1 - pct]).to(x.device)
+    both = torch.quantile(x, q, dim=dim)
+    return both[:n], both[n:]

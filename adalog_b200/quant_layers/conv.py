@@ -154,8 +154,8 @@ class AsymmetricallyBatchingQuantConv2d(PTQSLBatchingQuantConv2d):
         num_scale = int(self.eq_n / num_zp)
         pct = torch.tensor([l, r])
         w2 = self._weight2()
-        up = torch.quantile(w2, pct.to(w2.device), dim=-1).unsqueeze(-1)
-        lo = torch.quantile(w2, (1 - pct).to(w2.device), dim=-1).unsqueeze(-1)
+        up, lo = _fpcs.quantile_pair(w2, pct, -1)
+        up, lo = up.unsqueeze(-1), lo.unsqueeze(-1)
         return _fpcs.percentile_grid(up[0:1] - lo[0:1], up[1:] - lo[1:], nl, num_zp, num_scale, 0, 2)
 
     def weight_fpcs(self, fpcs_width=16, steps=4, search_strategy=None):

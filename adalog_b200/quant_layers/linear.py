@@ -210,8 +210,8 @@ class AsymmetricallyBatchingQuantLinear(PTQSLBatchingQuantLinear):
         num_scale = int(self.eq_n / num_zp)
         pct = torch.tensor([l, r])
         w3 = self._weight3()
-        up = torch.quantile(w3, pct.to(w3.device), dim=-1).unsqueeze(-1)
-        lo = torch.quantile(w3, (1 - pct).to(w3.device), dim=-1).unsqueeze(-1)
+        up, lo = _fpcs.quantile_pair(w3, pct, -1)
+        up, lo = up.unsqueeze(-1), lo.unsqueeze(-1)
         return _fpcs.percentile_grid(up[0:1] - lo[0:1], up[1:] - lo[1:], nl, num_zp, num_scale, 0, 3)
 
     def calculate_percentile_activation_candidates(self, l=0.9, r=1.0):
@@ -221,14 +221,17 @@ class AsymmetricallyBatchingQuantLinear(PTQSLBatchingQuantLinear):
         num_zp = min(16, nl * 2)
         num_scale = int(self.eq_n / num_zp)
         pct = torch.tensor([l, r])
-        x = adist.all_gather_cat(self._ctx.x2d.view(self._ctx.n_samples, -1))
-        if self.a_quantizer.channel_wise:
-            xc = x.reshape(-1, self.in_features)
-            up = torch.quantile(xc, pct.to(x.device), dim=0).transpose(0, 1)
-            lo = torch.quantile(xc, (1 - pct).to(x.device), dim=0).transpose(0, 1)
-        else:
-            up, lo = _fpcs.chunked_quantile(x.reshape(1, 1, -1), pct)
-            up, lo = up.transpose(0, 1), lo.transpose(0, 1)          # [1, 2]
+        # the calibration input of a module does not change between its search rounds: sort it once
+        key = (bool(self.a_quantizer.channel_wise), l, r)
+        cache = self._ctx.__dict__.setdefault('_pct_cache', {})
+        if key not in cache:
+            x = adist.all_gather_cat(self._ctx.x2d.view(self._ctx.n_samples, -1))
+            if self.a_quantizer.channel_wise:
+                up, lo = _fpcs.quantile_pair(x.reshape(-1, self.in_features), pct, 0)
+            else:
+                up, lo = _fpcs.chunked_quantile(x.reshape(1, 1, -1), pct)
+            cache[key] = (up.transpose(0, 1), lo.transpose(0, 1))    # [C|1, 2]
+        up, lo = cache[key]
         scales, zps = _fpcs.percentile_grid(up[:, 0:1] - lo[:, 0:1], up[:, 1:] - lo[:, 1:], nl, num_zp, num_scale, -1)
         return scales.clamp(min=1e-4), zps
 

@@ -138,13 +138,19 @@ class AsymmetricallyBatchingQuantMatMul(PTQSLBatchingQuantMatMul):
         num_zp = min(16, nl)
         num_scale = int(self.eq_n / num_zp)
         pct = torch.tensor([l, r])
-        x = adist.all_gather_cat(x)
-        if self.head_channel_wise:
-            x_ = x.transpose(0, 1).contiguous()
-            x_ = x_.view(x_.shape[0], 1, -1)
-        else:
-            x_ = x.reshape(1, 1, -1)
-        up, lo = _fpcs.chunked_quantile(x_, pct)
+        # the operands of a module do not change between its search rounds: sort each once
+        key = (x.data_ptr(), tuple(x.shape), x._version, bool(self.head_channel_wise), l, r)
+        cache = self.__dict__.setdefault('_pct_cache', {})
+        if key not in cache:
+            cache.clear()
+            xg = adist.all_gather_cat(x)
+            if self.head_channel_wise:
+                x_ = xg.transpose(0, 1).contiguous()
+                x_ = x_.view(x_.shape[0], 1, -1)
+            else:
+                x_ = xg.reshape(1, 1, -1)
+            cache[key] = _fpcs.chunked_quantile(x_, pct)
+        up, lo = cache[key]
         d_min = (up[0] - lo[0]).view(1, 1, -1, 1, 1)
         d_max = (up[1] - lo[1]).view(1, 1, -1, 1, 1)
         return _fpcs.percentile_grid(d_min, d_max, nl, num_zp, num_scale, 0, 4)

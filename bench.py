@@ -266,6 +266,7 @@ def run_ours(args):
         ms, wall, _, model = one_step(False)
         times.append(ms)
     gemm_flops, gemm_ms, gemm_launches = ops.profile_gemm_summary()
+    fz_flops, fz_ms, fz_launches = ops.profile_fused_summary()
     ops.profile_reset(False)
     launches = _lib.LAUNCHES['count']
     clocks = sampler.stop() if sampler else None
@@ -307,7 +308,14 @@ def run_ours(args):
                                  frac=achieved / peaks['tflops'] if peaks['tflops'] else None, traffic=None,
                                  peak_source=f"{peaks['src']} bf16_tflops_sustained",
                                  launches=gemm_launches, kernel_ms_per_step=gemm_ms / max(1, args.steps),
-                                 share_of_step=gemm_ms / max(1e-9, sum(times))))
+                                 share_of_step=gemm_ms / max(1e-9, sum(times)),
+                                 other_kernels=[dict(
+                                     kernel='fused_cand_gemm_err_kernel (attention sweeps: candidates generated in '
+                                            'shared memory + tcgen05 GEMM + error epilogue)',
+                                     bound='TMEM read-out (64 B/clk/SM) and issue slots, see DESIGN.md section 4',
+                                     launches=fz_launches, kernel_ms_per_step=fz_ms / max(1, args.steps),
+                                     achieved=fz_flops / (fz_ms / 1e3) / 1e12 if fz_ms > 0 else 0.0, unit='TFLOP/s',
+                                     share_of_step=fz_ms / max(1e-9, sum(times)))]))
         if e2e_ms is not None:
             out['e2e'] = dict(value=world * cands / (e2e_ms / 1e3), unit='candidates/s',
                               h2d_bytes_per_step=host_images.numel() * 4, d2h_bytes_per_step=d2h,
