@@ -25,11 +25,15 @@ def profile_reset(on):
     PROFILE['fused'] = []
 
 
-def profile_gemm_summary():
-    """(total algorithmic FLOPs, total ms, launches) of the candidate GEMM since profile_reset"""
-    flops = sum(f for _, _, f in PROFILE['gemm'])
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in PROFILE['gemm'])
-    return flops, ms, len(PROFILE['gemm'])
+def profile_gemm_summary(split=False):
+    """(flops, milliseconds, launches) of the candidate-GEMM launches recorded since profile_reset(True);
+    split=True: {'bf16': (...), 'i8': (...)} by operand type (int8 MMAs run at twice the bf16 rate)."""
+    torch.cuda.synchronize()
+    def tot(rows):
+        return sum(r[2] for r in rows), sum(r[0].elapsed_time(r[1]) for r in rows), len(rows)
+    if split:
+        return {'bf16': tot([r for r in PROFILE['gemm'] if not r[3]]), 'i8': tot([r for r in PROFILE['gemm'] if r[3]])}
+    return tot(PROFILE['gemm'])
 
 
 def _cuda(*ts):
@@ -259,7 +263,7 @@ def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, l
         e0.record()
         call('adalog_cand_gemm_err', ctypes.byref(a), _stream())
         e1.record()
-        PROFILE['gemm'].append((e0, e1, 2.0 * P_TILE * U * N * (k_true if k_true else ka)))
+        PROFILE['gemm'].append((e0, e1, 2.0 * P_TILE * U * N * (k_true if k_true else ka), bool(i8)))
     else:
         call('adalog_cand_gemm_err', ctypes.byref(a), _stream())
     return partial

@@ -37,6 +37,13 @@ MODEL_ALIASES = {'deit_tiny': 'deit_tiny_patch16_224', 'deit_small': 'deit_small
 DIMS = {'deit_tiny': (192, 3, 12), 'deit_small': (384, 6, 12), 'deit_base': (768, 12, 12), 'vit_base': (768, 12, 12),
         'vit_small': (384, 6, 12)}
 TOKENS = 197
+# dram__bytes_read.sum + dram__bytes_write.sum of one cand_gemm_err_kernel launch from the `ncu --set full` capture in
+# profiles/r1_ncu_full_cand_gemm_err_v2.json (a 1365-unit chunk of a K=3072, N=768 activation sweep: 1.074e9 B of
+# candidate operand + 4.7e6 B of fixed operand are the algorithmic bytes of that launch)
+NCU_TRAFFIC_BYTES = 1.087e9
+NCU_TRAFFIC_NOTE = ('per launch, ncu --set full of a K=3072 N=768 activation-sweep chunk (profiles/'
+                    'r1_ncu_full_cand_gemm_err_v2.json): 1.083 GB read + 4 MB written vs 1.079 GB algorithmic; tensor '
+                    'pipe 93% active in that launch')
 
 
 def parse():
@@ -266,6 +273,7 @@ def run_ours(args):
         ms, wall, _, model = one_step(False)
         times.append(ms)
     gemm_flops, gemm_ms, gemm_launches = ops.profile_gemm_summary()
+    gemm_split = ops.profile_gemm_summary(split=True)
     fz_flops, fz_ms, fz_launches = ops.profile_fused_summary()
     ops.profile_reset(False)
     launches = _lib.LAUNCHES['count']
@@ -297,7 +305,13 @@ def run_ours(args):
         ms_step = statistics.mean(times)
         value = world * cands / (ms_step / 1e3)
         peaks = load_peaks()
-        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        # int8 MMAs (tcgen05 kind::i8) run at twice the bf16 rate and MEASURED_PEAKS.json holds a bf16 peak only, so an
+        # int8 operation counts as half a bf16 FLOP: `achieved` is bf16-equivalent TFLOP/s = tensor-pipe occupancy x peak
+        bf, i8 = gemm_split['bf16'], gemm_split['i8']
+        achieved = (bf[0] + 0.5 * i8[0]) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        by_type = {k: dict(launches=v[2], kernel_ms_per_step=v[1] / max(1, args.steps),
+                           tera_ops_per_s=(v[0] / (v[1] / 1e3) / 1e12 if v[1] > 0 else 0.0))
+                   for k, v in gemm_split.items()}
         out = dict(metric='fpcs_candidates_per_s', value=value, unit='candidates/s', n_gpus=world, steps=args.steps,
                    warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
                    dtype='bf16 operands (exact integers) / f32 accumulate / f64 error sums', data='synthetic',
@@ -305,8 +319,11 @@ def run_ours(args):
                    calibration_wall_s=ms_step / 1e3, fakequant_img_per_s=fq_img_s, gpu_launches=launches, clocks=clocks,
                    roofline=dict(kernel='cand_gemm_err_kernel (tcgen05 candidate GEMM + fused error epilogue)',
                                  bound='tensor', achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s',
-                                 frac=achieved / peaks['tflops'] if peaks['tflops'] else None, traffic=None,
+                                 frac=achieved / peaks['tflops'] if peaks['tflops'] else None, traffic=NCU_TRAFFIC_BYTES,
+                                 traffic_note=NCU_TRAFFIC_NOTE,
                                  peak_source=f"{peaks['src']} bf16_tflops_sustained",
+                                 note='achieved = bf16-equivalent TFLOP/s (an int8 op counts 1/2: kind::i8 runs at 2x '
+                                      'the bf16 rate; the measured peak is bf16)', by_operand_type=by_type,
                                  launches=gemm_launches, kernel_ms_per_step=gemm_ms / max(1, args.steps),
                                  share_of_step=gemm_ms / max(1e-9, sum(times)),
                                  other_kernels=[dict(
