@@ -302,3 +302,67 @@ def test_non_default_search_settings(eq_n, fpcs):
     tap.report(f'eq_n={eq_n} fpcs={fpcs}')
     assert torch.equal(m.w_quantizer.scale.data, s.wq.scale) and torch.equal(m.a_quantizer.scale.data, s.aq.scale)
     assert torch.equal(m.w_quantizer.zero_point.data, s.wq.zero_point)
+
+
+@pytest.mark.parametrize('shape', [  # (images, heads, S1, Kd, S2): DeiT QK^T / P.V, Swin window QK^T / P.V, ragged
+    (4, 3, 197, 64, 197), (4, 3, 197, 197, 64), (6, 2, 49, 32, 49), (6, 2, 49, 49, 32), (2, 2, 144, 32, 144),
+    (3, 1, 50, 40, 70)])
+@pytest.mark.parametrize('bits', [3, 4, 6])
+def test_fused_matches_two_kernel_path(shape, bits, monkeypatch):
+    """The fused generator + GEMM kernel (candidate tile generated in shared memory) and the generator -> workspace ->
+    GEMM path evaluate the same integers: their similarities agree to FP32-summation-order noise, for the uniform
+    A / B sweeps and the post-softmax AdaLog base search, with P < 128 candidates as well."""
+    from adalog_b200 import sweep
+    from adalog_b200.quantizers import UniformQuantizer
+    Bn, H, S1, Kd, S2 = shape
+    torch.manual_seed(sum(shape) + bits)
+    A = torch.randn(Bn, H, S1, Kd, device=DEV)
+    Bm = torch.randn(Bn, H, Kd, S2, device=DEV)
+    out = A @ Bm
+    ctx = sweep.MatMulCtx(A, Bm, out)
+    nl = 2 ** (bits - 1)
+    for P in (128, 48):
+        cs, cz = O.matmul_candidates(A, nl, 128, True)
+        cs, cz = cs[:P].contiguous(), cz[:P].contiguous()
+        q = UniformQuantizer(bits)
+        q.scale, q.zero_point = cs[P // 2].clone(), cz[P // 2].clone().float()
+        res = {}
+        for fused in (True, False):
+            monkeypatch.setattr(sweep, 'FUSED', fused)
+            monkeypatch.setattr(sweep, '_use_fused', (lambda K, N, i8, log, n: True) if fused else (lambda *a: False))
+            res[fused] = (sweep.matmul_err_A(ctx, q, cs, cz, nl, True), sweep.matmul_err_B(ctx, q, cs, cz, nl, True))
+        for f, u in zip(res[True], res[False]):
+            assert torch.allclose(f, u, rtol=2e-6, atol=0), (f - u).abs().max().item()
+    # post-softmax AdaLog base search (unscaled log candidates)
+    p = torch.softmax(torch.randn(Bn, H, S1, Kd, device=DEV) * 3, -1)
+    pctx = sweep.MatMulCtx(p, Bm, p @ Bm)
+    qc = torch.arange(10, 138, device=DEV).view(-1, 1, 1, 1, 1)
+    Bq = UniformQuantizer(bits)
+    Bq.scale, Bq.zero_point = cs[0].clone(), cz[0].clone().float()
+    res = {}
+    for fused in (True, False):
+        monkeypatch.setattr(sweep, '_use_fused', (lambda K, N, i8, log, n: True) if fused else (lambda *a: False))
+        res[fused] = sweep.matmul_err_A_log_base(pctx, Bq, qc, nl)
+    assert torch.allclose(res[True], res[False], rtol=2e-6, atol=0), (res[True] - res[False]).abs().max().item()
+
+
+def test_fused_int8_operands():
+    """kind::i8 flavour of the fused kernel (int8 candidate tile packed from the magic-number bits, int8 fixed operand):
+    same similarities as the bf16 flavour"""
+    from adalog_b200 import ops, sweep
+    Bn, H, S1, Kd, S2, nl = 3, 2, 197, 64, 197, 8
+    torch.manual_seed(11)
+    A = torch.randn(Bn, H, S1, Kd, device=DEV)
+    Bm = torch.randn(Bn, H, Kd, S2, device=DEV)
+    ctx = sweep.MatMulCtx(A, Bm, A @ Bm)
+    cs, cz = O.matmul_candidates(A, nl, 128, True)
+    c2, z2 = sweep._cand2d(cs, cz)
+    sB, zB = c2[64].contiguous(), z2[64].contiguous()
+    rs = (sweep._pad128(c2.t().contiguous()).double() * sB.double().reshape(H, 1)).float().contiguous()
+    U = Bn * H * S1
+    out = {}
+    for i8 in (False, True):
+        fixed, _ = ops.gen_uniform_fixed(ctx.Bt2d, sB, zB, S2, H, nl, i8=i8)
+        out[i8] = sweep._run_fused(ctx.A2d, Kd, fixed, S2, U, S1, ctx.y2d, S2, rs, H, nl, 128, i8=i8, cs=c2, cz=z2,
+                                   pstride=c2.shape[1], gstride=1, g_div=S1, g_mod=H)
+    assert torch.allclose(out[True], out[False], rtol=1e-9, atol=0), (out[True] - out[False]).abs().max().item()
