@@ -46,17 +46,20 @@ __global__ void __launch_bounds__(256) uniform_fakequant_kernel(const float* __r
                                                                int64_t ngroups, int nl, int sym) {
   const bool single = ngroups == 1;
   const float s0 = scale[0], z0 = (zp != nullptr) ? zp[0] : 0.0f;
+  const float two_n = (float)(2 * nl), inv2n = 1.0f / two_n, L = (float)(2 * nl - 1);
+  const bool pow2 = !sym && nl > 0 && (nl & (nl - 1)) == 0;     // r/2n etc. are exact scalings only then
   if (VEC4) {
     constexpr int UNR = 4;
     const IdxT n4 = (IdxT)(n >> 2);
     const IdxT inner4 = (IdxT)(inner >> 2), ng = (IdxT)ngroups;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const IdxT stride = (IdxT)gridDim.x * blockDim.x;
-    for (IdxT base = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * UNR) {
-      float4 v[UNR];
-      float sv[UNR], zv[UNR];
+    // software pipelined: the loads of iteration k+1 are in flight while iteration k is computed, so a thread always
+    // has UNR 16-byte loads outstanding (with the loads issued only between compute phases the kernel sat at 75% of
+    // the bandwidth a plain copy kernel reaches: not enough bytes in flight per SM)
+    auto load_set = [&](IdxT base, float4 (&v)[UNR], float (&sv)[UNR], float (&zv)[UNR]) {
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {                      // all loads (data, scale, zero point) issued up front
+      for (int u = 0; u < UNR; ++u) {
         const IdxT i = base + (IdxT)u * stride;
         sv[u] = s0; zv[u] = z0;
         if (i < n4) {
@@ -68,19 +71,46 @@ __global__ void __launch_bounds__(256) uniform_fakequant_kernel(const float* __r
           }
         }
       }
+    };
+    float4 v[UNR], vn[UNR];
+    float sv[UNR], zv[UNR], svn[UNR], zvn[UNR];
+    const IdxT base0 = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
+    if (base0 < n4) load_set(base0, v, sv, zv);
+    for (IdxT base = base0; base < n4; base += stride * UNR) {
+      const IdxT nbase = base + stride * UNR;
+      if (nbase < n4 && nbase > base) load_set(nbase, vn, svn, zvn);
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         const IdxT i = base + (IdxT)u * stride;
         if (i >= n4) break;
         const float s = sv[u], z = zv[u];
         float4 o; float c0, c1, c2, c3;
-        uq_fwd(v[u].x, s, z, nl, sym, o.x, c0);
-        uq_fwd(v[u].y, s, z, nl, sym, o.y, c1);
-        uq_fwd(v[u].z, s, z, nl, sym, o.z, c2);
-        uq_fwd(v[u].w, s, z, nl, sym, o.w, c3);
+        // exact fast path of the generators (quant_device.cuh: uq_code_fast), four elements branch-free, one rare
+        // IEEE redo per float4: r = fl(1/s), clamp by the FMA's saturation, rint by the 1.5*2^23 trick
+        const float r = __fdiv_rn(1.0f, s);
+        const bool fast = pow2 && z == rintf(z) && z >= 0.0f && z <= L && fabsf(r) <= 3.0e38f;
+        const float4 cc = make_float4(r * inv2n, z * inv2n, L * inv2n, kMagic);
+        bool unsafe = !fast;
+        const float t0 = uq_code_fast(v[u].x, cc, two_n, kFracSafe, unsafe);
+        const float t1 = uq_code_fast(v[u].y, cc, two_n, kFracSafe, unsafe);
+        const float t2 = uq_code_fast(v[u].z, cc, two_n, kFracSafe, unsafe);
+        const float t3 = uq_code_fast(v[u].w, cc, two_n, kFracSafe, unsafe);
+        unsafe |= !(v[u].x == v[u].x && v[u].y == v[u].y && v[u].z == v[u].z && v[u].w == v[u].w);   // NaN
+        if (!unsafe) {
+          c0 = __fsub_rn(t0, kMagic); c1 = __fsub_rn(t1, kMagic); c2 = __fsub_rn(t2, kMagic); c3 = __fsub_rn(t3, kMagic);
+          o.x = __fmul_rn(__fsub_rn(c0, z), s); o.y = __fmul_rn(__fsub_rn(c1, z), s);
+          o.z = __fmul_rn(__fsub_rn(c2, z), s); o.w = __fmul_rn(__fsub_rn(c3, z), s);
+        } else {
+          uq_fwd(v[u].x, s, z, nl, sym, o.x, c0);
+          uq_fwd(v[u].y, s, z, nl, sym, o.y, c1);
+          uq_fwd(v[u].z, s, z, nl, sym, o.z, c2);
+          uq_fwd(v[u].w, s, z, nl, sym, o.w, c3);
+        }
         if (y) reinterpret_cast<float4*>(y)[i] = o;
         if (codes) reinterpret_cast<short4*>(codes)[i] = make_short4((short)c0, (short)c1, (short)c2, (short)c3);
       }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { v[u] = vn[u]; sv[u] = svn[u]; zv[u] = zvn[u]; }
     }
   } else {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -125,7 +155,8 @@ __global__ void __launch_bounds__(256) log_fakequant_kernel(const float* __restr
                                                            const long long* __restrict__ q,
                                                            const float* __restrict__ table1,
                                                            const float* __restrict__ table2,
-                                                           const float* __restrict__ shift, int sub_shift) {
+                                                           const float* __restrict__ shift, int sub_shift,
+                                                           uint32_t magic4) {
   __shared__ float lutv[260];
   const int ncode = 2 * nl;
   const float s = scale[0];
@@ -151,43 +182,68 @@ __global__ void __launch_bounds__(256) log_fakequant_kernel(const float* __restr
   const float r = __fdiv_rn(1.0f, s);
   const float kq = (kind == 0) ? 1.0f : (kind == 1 ? 2.0f : __fdiv_rn(37.0f, qf));
   const float ncf = (float)ncode;
-  auto one = [&](float xin, float& yo, float& co) {
-    const float xv = shift ? __fadd_rn(xin, sh) : xin;
+  // fast part: t = -lg2(clamp((x+shift)*r, 1e-15, 1)) * k (>= 0, so only the upper clamp is needed), tm = t + 1.5*2^23
+  // (the code in the low mantissa bits), `unsafe` when t is within m(t) of a half-integer or NaN
+  auto fast = [&](float xin, float& xv, bool& unsafe) -> float {
+    xv = shift ? __fadd_rn(xin, sh) : xin;
     const float vp = fminf(fmaxf(__fmul_rn(xv, r), 1e-15f), 1.0f);
-    const float t = fminf(fmaxf(__fmul_rn(-__log2f(vp), kq), 0.0f), ncf);
-    const float tm = __fadd_rn(t, 12582912.0f);
-    float c = __fsub_rn(tm, 12582912.0f);
-    const float f = fabsf(__fsub_rn(t, c));
-    // (the two clamps of v are continuous, so they need no special case; NaN fails the comparison and takes the
-    // IEEE chain like everything near a rounding boundary)
-    if (!(f <= 0.5f - (5e-6f + 1.5e-6f * t))) {
-      c = log_code_exact(xv, s, kind, qf);
-      c = (c < ncf) ? fmaxf(c, 0.0f) : ncf;                  // >= 2n (incl. +inf, NaN): masked entry
-      if (!(c >= 0.0f)) c = ncf;
-    }
-    float d = lutv[(int)c];
+    const float t = fminf(__fmul_rn(-__log2f(vp), kq), ncf);
+    const float tm = __fadd_rn(t, kMagic);
+    const float f = fabsf(__fsub_rn(t, __fsub_rn(tm, kMagic)));
+    unsafe |= !(f <= fmaf(-1.5e-6f, t, 0.5f - 5e-6f));
+    return tm;
+  };
+  // IEEE chain for one element; returns the LUT index as tm
+  auto exact = [&](float xv) -> float {
+    float c = log_code_exact(xv, s, kind, qf);
+    c = (c < ncf) ? fmaxf(c, 0.0f) : ncf;                      // >= 2n (incl. +inf, NaN): masked entry
+    if (!(c >= 0.0f)) c = ncf;
+    return __fadd_rn(c, kMagic);
+  };
+  const uint32_t lut_bias = (uint32_t)__cvta_generic_to_shared(lutv) - magic4;
+  auto finish = [&](float tm, float& yo, float& co) {
+    float d;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(d) : "r"(__float_as_uint(tm) * 4u + lut_bias));
     if (sub_shift) d = __fsub_rn(d, sh);
     yo = d;
-    co = fminf(c, ncf - 1.0f);                               // the reference clamps the stored code to 2n-1
+    co = fminf(__fsub_rn(tm, kMagic), ncf - 1.0f);             // the reference clamps the stored code to 2n-1
+  };
+  auto one = [&](float xin, float& yo, float& co) {
+    float xv; bool unsafe = false;
+    float tm = fast(xin, xv, unsafe);
+    if (unsafe) tm = exact(xv);
+    finish(tm, yo, co);
   };
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (VEC4) {
     constexpr int UNR = 4;
     const int64_t n4 = n >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * UNR) {
-      float4 v[UNR];
+    // software pipelined like uniform_fakequant_kernel: iteration k+1's loads are in flight during iteration k's math
+    float4 v[UNR], vn[UNR];
+    const int64_t base0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) if (base + u * stride < n4) v[u] = __ldg(x4 + base + u * stride);
+    for (int u = 0; u < UNR; ++u) if (base0 + u * stride < n4) v[u] = __ldg(x4 + base0 + u * stride);
+    for (int64_t base = base0; base < n4; base += stride * UNR) {
+      const int64_t nbase = base + stride * UNR;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) if (nbase + u * stride < n4) vn[u] = __ldg(x4 + nbase + u * stride);
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         const int64_t i = base + u * stride;
         if (i >= n4) break;
         float4 o; float c0, c1, c2, c3;
-        one(v[u].x, o.x, c0); one(v[u].y, o.y, c1); one(v[u].z, o.z, c2); one(v[u].w, o.w, c3);
+        // four elements branch-free (their dependency chains interleave), one rare IEEE redo per float4
+        float x0, x1, x2, x3; bool unsafe = false;
+        float t0 = fast(v[u].x, x0, unsafe), t1 = fast(v[u].y, x1, unsafe);
+        float t2 = fast(v[u].z, x2, unsafe), t3 = fast(v[u].w, x3, unsafe);
+        if (unsafe) { t0 = exact(x0); t1 = exact(x1); t2 = exact(x2); t3 = exact(x3); }
+        finish(t0, o.x, c0); finish(t1, o.y, c1); finish(t2, o.z, c2); finish(t3, o.w, c3);
         if (y) reinterpret_cast<float4*>(y)[i] = o;
         if (codes) reinterpret_cast<short4*>(codes)[i] = make_short4((short)c0, (short)c1, (short)c2, (short)c3);
       }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) v[u] = vn[u];
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -693,6 +749,18 @@ static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
+// grid of a grid-stride streaming kernel: exactly the number of CTAs that are resident at once (occupancy x 148), so all
+// CTAs run in ONE wave and do equal shares.  (148 x 8 CTAs of 256 threads at 48 registers were 1.6 waves: the second,
+// partly filled wave cost ~20% of the HBM bandwidth.)
+template <typename K>
+static int resident_grid(K kernel, int64_t work_items, int threads, size_t smem = 0) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 4;
+  const int64_t need = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)kNumSMs * occ;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
 }  // namespace adalog
 
 using namespace adalog;
@@ -713,10 +781,10 @@ int adalog_uniform_fakequant_f32(const float* x, float* y, int16_t* codes, int64
   const bool vec = aligned && (n % 4 == 0) && (ngroups == 1 || inner % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   if (vec && n < (1ll << 31))
-    uniform_fakequant_kernel<true, uint32_t><<<grid_for(n / 16, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
+    uniform_fakequant_kernel<true, uint32_t><<<resident_grid(uniform_fakequant_kernel<true, uint32_t>, n / 16, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
                                                                                     ngroups, n_levels, symmetric);
   else if (vec)
-    uniform_fakequant_kernel<true, uint64_t><<<grid_for(n / 16, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
+    uniform_fakequant_kernel<true, uint64_t><<<resident_grid(uniform_fakequant_kernel<true, uint64_t>, n / 16, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
                                                                                     ngroups, n_levels, symmetric);
   else
     uniform_fakequant_kernel<false, uint64_t><<<grid_for(n, 256), 256, 0, st>>>(x, y, codes, n, scale, zp, inner,
@@ -735,11 +803,11 @@ int adalog_log_fakequant_f32(const float* x, float* y, int16_t* codes, int64_t n
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(codes) & 7) == 0 && (n % 4 == 0);
   if (vec)
-    log_fakequant_kernel<true><<<grid_for(n / 16, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, y, codes, n, scale, kind, n_levels, q, table1, table2, shift, sub_shift);
+    log_fakequant_kernel<true><<<resident_grid(log_fakequant_kernel<true>, n / 16, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, y, codes, n, scale, kind, n_levels, q, table1, table2, shift, sub_shift, 0x2D000000u);
   else
     log_fakequant_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, y, codes, n, scale, kind, n_levels, q, table1, table2, shift, sub_shift);
+        x, y, codes, n, scale, kind, n_levels, q, table1, table2, shift, sub_shift, 0x2D000000u);
   return check_launch("log_fakequant");
 }
 

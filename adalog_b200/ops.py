@@ -91,18 +91,31 @@ def group_layout(x_shape, s_shape):
 
 
 # ------------------------------------------------------------------------------------------ forwards
+def _round_ste_cached(zero_point, sc):
+    """round_ste(zero_point) (_ste.py:5-6: (z.round() - z) + z in FP32) as a flat tensor matching `sc`; remembered on
+    the zero-point tensor itself until it is modified, so an inference forward is ONE kernel launch, not four."""
+    key = (zero_point.data_ptr(), zero_point._version, sc.numel())
+    hit = getattr(zero_point, '_adalog_zr', None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    z = _f32(zero_point.detach()).reshape(-1)
+    zr = (z.round() - z) + z
+    if zr.numel() != sc.numel():
+        zr = zr.expand_as(sc).contiguous()
+    try:
+        zero_point._adalog_zr = (key, zr)
+    except AttributeError:
+        pass
+    return zr
+
+
 def uniform_fakequant(x, scale, zero_point, n_levels, sym=False, want_codes=False, want_y=True):
     """quantizers/uniform.py:25-36 on device."""
     _cuda(x, scale, zero_point)
     xc = _f32(x)
     inner, ngroups = group_layout(xc.shape, scale.shape)
     sc = _f32(scale.detach()).reshape(-1)
-    zr = None
-    if not sym:
-        z = _f32(zero_point.detach()).reshape(-1)
-        zr = (z.round() - z) + z                       # round_ste, _ste.py:5-6
-        if zr.numel() != sc.numel():
-            zr = zr.expand_as(sc).contiguous()
+    zr = None if sym else _round_ste_cached(zero_point, sc)
     y = torch.empty_like(xc) if want_y else None
     codes = torch.empty(xc.shape, dtype=torch.int16, device=xc.device) if want_codes else None
     call('adalog_uniform_fakequant_f32', _p(xc), _p(y), _p(codes), xc.numel(), _p(sc), _p(zr), inner, ngroups,
