@@ -65,6 +65,7 @@ SIGNATURES = {
     'adalog_cand_gemm_err': [ctypes.POINTER(GemmErrArgs), c_vp],
     'adalog_fused_cand_gemm_err_grid': [ctypes.POINTER(FusedArgs)],
     'adalog_fused_cand_gemm_err': [ctypes.POINTER(FusedArgs), c_vp],
+    'adalog_gemm_dequant': [ctypes.POINTER(GemmErrArgs), c_vp, c_i64, c_i64, c_vp],
     'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
 }
 

@@ -63,12 +63,16 @@ struct KArgs {
   const float* cs; const float* cb;
   double* partial;
   float* dbg;   // debug mode: dump D[128, N] of the single tile
+  float* out; long long ldo; long long m_rows;   // MODE_STORE: output matrix [m_rows, N], row pitch ldo
 };
 
 // ---------------------------------------------------------------- the kernel
 // MODE_CS: yhat = rs*(cs[n]*D), y' = y - cb[n] (linear A-side sweeps); MODE_RB: yhat = rs*D + rb (W-side sweeps);
 // MODE_PLAIN: yhat = rs*D (attention matmuls)
-enum { MODE_CS = 0, MODE_RB = 1, MODE_PLAIN = 2, MODE_NOEPI = 3 /* diagnostic: pipeline only, no epilogue math */ };
+// MODE_STORE: no error at all -- out[u*128+p, n] = rs*cs[n]*D + cb[n] is written (the fake-quant INFERENCE forward of a
+// linear layer: rows p of unit u are 128 consecutive tokens, not candidates)
+enum { MODE_CS = 0, MODE_RB = 1, MODE_PLAIN = 2, MODE_NOEPI = 3 /* diagnostic: pipeline only, no epilogue math */,
+       MODE_STORE = 4 };
 
 template <int MODE, bool DEBUG, bool I8>
 // 152 registers x 320 threads leave 16.9k registers of the SM free: one 256-thread generator CTA (64 registers) of the
@@ -168,7 +172,8 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== epilogue: TMEM -> registers -> per-candidate squared error =====================
     // 8 warps: warp w reads TMEM lanes 32*(w%4)..+31 (candidate p = that lane); group eg = (w-2)/4 takes the 32-column
     // slabs with index == eg (mod 2).  Every candidate therefore has two partial sums, folded in fixed order at the end.
-    constexpr bool HAS_CS = MODE == MODE_CS;
+    constexpr bool HAS_CS = MODE == MODE_CS || MODE == MODE_STORE;   // column scale / bias staged per CTA
+    constexpr bool STORE = MODE == MODE_STORE;
     const int ew = warp - kEpiWarp0;
     const int eg = ew >> 2;                                 // column group 0..kEpiGroups-1
     const int et = ((warp & 3) << 5) | lane;                // 0..127 = candidate p = TMEM lane (a warp reaches lanes 32*(warp%4)..)
@@ -205,7 +210,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int i = 0; i < kSlabsPerGroup; ++i) {
         const int c = (eg + i * G) * 32 + lane;
         const int n = n0 + c;
-        yreg[i] = (c < a.BN && n < a.N) ? __ldg(a.y + (long long)u * a.ldy + n) : 0.0f;
+        yreg[i] = (!STORE && c < a.BN && n < a.N) ? __ldg(a.y + (long long)u * a.ldy + n) : 0.0f;
       }
     };
     // four independent accumulators (same instruction sequence for every lane = candidate, so equal candidates still
@@ -213,6 +218,9 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     float acc4[4];
     // accumulator word -> FP32: kind::f16 accumulates in FP32, kind::i8 in S32 (exact integer dot products)
     auto accf = [](uint32_t w) -> float { return I8 ? __int2float_rn((int)w) : __uint_as_float(w); };
+    float* orow = nullptr;   // MODE_STORE: this thread's output row (nullptr beyond m_rows)
+    int ocol = 0;            // MODE_STORE: output column of the current slab's column 0
+    const bool ovec = STORE && (a.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
     // four columns j..j+3 of a slab staged at local offset l0; MASKED: columns >= lim contribute nothing
     auto quad = [&](auto masked, const uint32_t (&d)[32], int j, int l0, int cc, int lim, float rs, float rb) {
       constexpr bool MASKED = decltype(masked)::value;
@@ -222,6 +230,25 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (HAS_CS) {
         const float4 cv = *reinterpret_cast<const float4*>(&tail_s.cs_all[cc + j]);
         c4[0] = cv.x; c4[1] = cv.y; c4[2] = cv.z; c4[3] = cv.w;
+      }
+      if (STORE) {
+        // rb carries the output row pointer's validity through `orow` (set per tile); columns beyond N are not written
+        const float4 bv = *reinterpret_cast<const float4*>(&tail_s.cb_all[cc + j]);
+        float4 o;
+        o.x = fmaf(rs * c4[0], accf(d[j + 0]), bv.x); o.y = fmaf(rs * c4[1], accf(d[j + 1]), bv.y);
+        o.z = fmaf(rs * c4[2], accf(d[j + 2]), bv.z); o.w = fmaf(rs * c4[3], accf(d[j + 3]), bv.w);
+        if (orow != nullptr) {
+          float* dst = orow + ocol + j;
+          if (!MASKED || j + 3 < lim) {
+            if (ovec) *reinterpret_cast<float4*>(dst) = o;
+            else { dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w; }
+          } else {
+            if (j + 0 < lim) dst[0] = o.x;
+            if (j + 1 < lim) dst[1] = o.y;
+            if (j + 2 < lim) dst[2] = o.z;
+          }
+        }
+        return;
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -241,6 +268,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int j = 0; j < 32; ++j)
           if (c0 + j < ncols) a.dbg[(long long)et * a.N + n0 + c0 + j] = accf(d[j]);
       }
+      ocol = c0;
       if (MODE == MODE_NOEPI) {
         acc4[0] += __uint_as_float(d[0]);
       } else if (lim >= 32) {
@@ -267,6 +295,10 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int toff = cnt * a.BN;               // this tile's columns inside cs_all / cb_all
       const int ncols = min(a.BN, a.N - n0);
       const long long ri_t = ri;
+      if (STORE) {
+        const long long row = (a.u_base + cu) * kBM + et;
+        orow = row < a.m_rows ? a.out + row * a.ldo + n0 : nullptr;
+      }
       // advance to tile t+1
       if (++cnt == n_nt) {
         cnt = 0; ++cu;
@@ -349,8 +381,10 @@ static int validate(const adalog_gemm_err_args* a, bool need_partial) {
   return 0;
 }
 
-static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st) {
+static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st, float* out = nullptr, long long ldo = 0,
+                  long long m_rows = 0) {
   KArgs k;
+  k.out = out; k.ldo = ldo; k.m_rows = m_rows;
   k.KB = a->KB; k.N = a->N; k.BN = a->BN; k.NT = (a->N + a->BN - 1) / a->BN; k.U = a->U; k.UG = a->UG; k.upc = a->upc;
   k.cpg = (a->UG + a->upc - 1) / a->upc;
   k.brpg = a->brpg; k.g_base = a->g_base; k.u_base = a->u_base;
@@ -371,7 +405,10 @@ static int launch(const adalog_gemm_err_args* a, float* dbg, cudaStream_t st) {
                          (int)kSmemBytes);                                                                    \
     cand_gemm_err_kernel<MD, DBG, I8><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, k);                       \
   } while (0)
-  if (i8) {
+  if (out) {
+    if (i8) ADALOG_LAUNCH_GEMM(MODE_STORE, false, true);
+    else    ADALOG_LAUNCH_GEMM(MODE_STORE, false, false);
+  } else if (i8) {
     if (dbg)         ADALOG_LAUNCH_GEMM(MODE_PLAIN, true, true);
     else if (a->cs)  ADALOG_LAUNCH_GEMM(MODE_CS, false, true);
     else if (a->rb)  ADALOG_LAUNCH_GEMM(MODE_RB, false, true);
@@ -403,6 +440,20 @@ int adalog_cand_gemm_err(const adalog_gemm_err_args* a, void* stream) {
   int rc = validate(a, true);
   if (rc) return rc;
   return launch(a, nullptr, (cudaStream_t)stream);
+}
+
+int adalog_gemm_dequant(const adalog_gemm_err_args* a, float* out, int64_t ldo, int64_t m_rows, void* stream) {
+  ADALOG_REQUIRE(a && out && m_rows > 0 && ldo >= a->N, -1, "gemm_dequant: bad output");
+  ADALOG_REQUIRE(a->A && a->Bm && a->rs && a->cs && a->cb && a->KB > 0 && a->N > 0 && a->U > 0 && a->UG == a->U &&
+                     a->upc > 0 && a->S > 0 && (int64_t)a->U * kBM >= m_rows && a->rs_div > 0 && a->rs_mod > 0, -1,
+                 "gemm_dequant: bad arguments (one group, U = ceil(m_rows / 128), rs / cs / cb required)");
+  ADALOG_REQUIRE(a->BN >= 16 && a->BN <= kMaxBN && a->BN % 16 == 0, -1, "gemm_dequant: BN must be a multiple of 16 in [16,256]");
+  ADALOG_REQUIRE(a->dtype == ADALOG_BF16 || a->dtype == ADALOG_I8, -1, "gemm_dequant: dtype");
+  ADALOG_REQUIRE(a->order == ADALOG_ORDER_UNIT_FAST || a->order == ADALOG_ORDER_SPLIT_FAST, -1, "gemm_dequant: order");
+  const int NT = (a->N + a->BN - 1) / a->BN;
+  ADALOG_REQUIRE(a->S <= NT && ((NT + a->S - 1) / a->S) * a->BN <= kCsCols, -1,
+                 "gemm_dequant: a CTA covers at most 1024 columns (raise S)");
+  return launch(a, nullptr, (cudaStream_t)stream, out, ldo, m_rows);
 }
 
 int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, int dtype, void* stream) {

@@ -282,6 +282,28 @@ def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, l
     return partial
 
 
+def gemm_dequant(A, m_rows, Bm, ka, N, rs, cs, cb, upc, S, i8=False, split_fast=False, out=None):
+    """out[m, n] = rs * cs[n] * (A[m, :] . Bm[n, :]) + cb[n] through the tcgen05 pipeline (adalog_gemm_dequant): the
+    fake-quant inference forward of a linear layer on the integer parts of Q_a(x) [m_rows, ka] and Q_w(W) [N, ka]."""
+    _cuda(A, Bm, rs, cs, cb)
+    BN = pick_bn(N)
+    U = (m_rows + P_TILE - 1) // P_TILE
+    a = GemmErrArgs()
+    a.A, a.Bm = A.data_ptr(), Bm.data_ptr()
+    a.a_rows, a.b_rows = int(m_rows), int(Bm.shape[0])
+    a.KB = ka // (2 * BK if i8 else BK)
+    a.dtype = I8 if i8 else BF16
+    a.order = 1 if split_fast else 0
+    a.N, a.BN, a.U, a.UG, a.upc, a.S = int(N), int(BN), int(U), int(U), int(upc), int(S)
+    a.brpg, a.g_base, a.u_base = 0, 0, 0
+    a.rs, a.rs_div, a.rs_mod = rs.data_ptr(), 1 << 62, 1
+    a.cs, a.cb = cs.data_ptr(), cb.data_ptr()
+    if out is None:
+        out = torch.empty(m_rows, N, dtype=torch.float32, device=A.device)
+    call('adalog_gemm_dequant', ctypes.byref(a), _p(out), int(out.stride(0)), int(m_rows), _stream())
+    return out
+
+
 SMEM_LIMIT = 227 * 1024 - 9600   # dynamic shared memory the fused kernel may ask for (its static part is ~9 KB)
 
 

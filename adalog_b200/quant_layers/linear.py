@@ -7,6 +7,8 @@ What differs is underneath: every `_search_best_*` evaluation is one fused devic
 libadalog_b200.so) over HBM-resident calibration tensors instead of a Python loop over 32-sample batches and
 candidate chunks, and the refinement loop is the shared driver in _fpcs.py.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -21,6 +23,7 @@ __all__ = ['MinMaxQuantLinear', 'PTQSLQuantLinear', 'PTQSLBatchingQuantLinear', 
            'AsymmetricallyChannelWiseBatchingQuantLinear', 'PostGeluTwinUniformBatchingQuantLinear',
            'PostGeluLogBasedBatchingQuantLinear']
 
+TC_FORWARD = os.environ.get('ADALOG_B200_TC_FORWARD', '1') == '1'   # tensor-core inference forward (see quant_forward)
 GELU_MIN = 0.16997124254703522     # -min GELU(x); the post-GELU shift (reference linear.py:749)
 
 
@@ -93,6 +96,26 @@ class PTQSLQuantLinear(MinMaxQuantLinear):
     def quant_weight_bias(self):
         w_sim = self.w_quantizer(self._weight3()).view(self.out_features, self.in_features)
         return w_sim, self.bias if self.bias is not None else None
+
+    def quant_forward(self, x):
+        """reference linear.py:46-51 with :90-92.  Inference (no grad, quantizers not in training_mode, CUDA): one exact
+        integer GEMM on the tensor cores with the dequantisation in its epilogue (sweep.linear_quant_forward; the
+        weight operand is cached until the weight or its quantizer changes).  Anything else -- BRECQ's STE training
+        branches, per-channel activation quantizers before reparam, the PTQ4ViT twin quantizer -- takes the
+        reference's own composition of fake-quant tensors and F.linear."""
+        assert self.calibrated, f"Module should be calibrated before run quant_forward for {self}"
+        if (TC_FORWARD and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+                and not self.w_quantizer.training_mode and not self.a_quantizer.training_mode
+                and self.w_quantizer.n_bits < 32 and self.a_quantizer.n_bits < 32):
+            cache = self.__dict__.setdefault('_tc_cache', {})
+            x2d = x.reshape(-1, self.in_features)
+            if not x2d.is_contiguous():
+                x2d = x2d.contiguous()
+            out = sweep.linear_quant_forward(x2d, self._weight3(), self.bias, self.w_quantizer, self.a_quantizer, cache)
+            if out is not None:
+                return out.view(*x.shape[:-1], self.out_features)
+        w_sim, bias_sim = self.quant_weight_bias()
+        return F.linear(self.quant_input(x), w_sim, bias_sim)
 
 
 class PTQSLBatchingQuantLinear(PTQSLQuantLinear):

@@ -303,6 +303,58 @@ def _fixed_weight_operand(weight3, wq, i8=False):
     return Bm, s, colsum
 
 
+def linear_quant_forward(x2d, weight3, bias, wq, aq, cache=None):
+    """F.linear(Q_a(x), Q_w(W), b) of the inference forward (linear.py:46-51, :90-92) as ONE exact integer GEMM on the
+    tensor cores: integer part of Q_a(x) (int8 when both quantizers have <= 7 bits, else bf16; AdaLog: m 2^-e in
+    bf16) x integer part of Q_w(W), dequantised in the epilogue  out = s_a s_w[n] D + b[n]  (the post-GELU shift
+    enters the bias: sum_k (v s - shift) w = s sum_k v w - shift sum_k w).  Returns None when the quantizer pair has
+    no exact operand form (the caller then takes the generic torch path).  `cache`: dict kept by the module for the
+    weight operand, which only changes when the weight or its quantizer parameters do."""
+    n_V, rows, in_f = weight3.shape
+    out_f = n_V * rows
+    is_log = getattr(aq, 'is_log', False)
+    if getattr(wq, 'sym', False) or wq.scale.numel() != out_f or wq.n_levels > 128:
+        return None
+    if is_log:
+        if not hasattr(aq, 'table2') or aq.scale.numel() != 1 or 2 * aq.n_levels > 64:
+            return None
+    elif getattr(aq, 'sym', False) or aq.scale.numel() != 1 or aq.n_levels > 128 or type(aq).__name__ != 'UniformQuantizer':
+        return None
+    i8 = not is_log and _i8_ok(aq.n_levels, wq.n_levels)
+    key = (weight3.data_ptr(), weight3._version, wq.scale.data_ptr(), wq.scale._version, wq.zero_point.data_ptr(),
+           wq.zero_point._version, i8)
+    if cache is not None and cache.get('key') == key:
+        Bm, s_w, colsum = cache['val']
+    else:
+        Bm, s_w, colsum = _fixed_weight_operand(weight3, wq, i8)
+        if colsum is None and is_log:
+            colsum = None
+        if cache is not None:
+            cache['key'], cache['val'] = key, (Bm, s_w, colsum)
+    dev = weight3.device
+    b = _f32(bias) if bias is not None else torch.zeros(out_f, device=dev)
+    M = x2d.shape[0]
+    if is_log:
+        nl = aq.n_levels
+        m2 = torch.round(_f32(aq.table2) * (4 * nl - 2))
+        A = ops.gen_log_fixed(x2d, aq.scale, aq.q, aq.shift, aq.table1, m2, nl)
+        a_scale = _f32(aq.scale).double().reshape(1) / (4 * nl - 2)
+        if not bool(getattr(aq, 'bias_reparamed', False)):
+            b = (b.double() - _f32(aq.shift).double().reshape(1) * s_w.double() * colsum.double()).float()
+    else:
+        s_a, z_a = uniform_operand_params(aq)
+        A, _ = ops.gen_uniform_fixed(x2d, s_a, z_a, 1 << 62, 1, aq.n_levels, i8=i8)
+        a_scale = s_a.double()
+    ka = ops.kpad(in_f, i8)
+    rs = a_scale.float().expand(ops.P_TILE).contiguous()
+    BN = ops.pick_bn(out_f)
+    NT = (out_f + BN - 1) // BN
+    U = (M + ops.P_TILE - 1) // ops.P_TILE
+    _, upc, _, S, sf = _launch_plan(U, U, NT, out_f * ka * (1 if i8 else 2), ops.P_TILE * ka * (1 if i8 else 2),
+                                    max((ka // 64) * BN * (1 if i8 else 2), 8 * BN), 1024 // BN)
+    return ops.gemm_dequant(A, M, Bm, ka, out_f, rs, s_w.contiguous(), b.contiguous(), upc, S, i8, sf)
+
+
 def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
     """linear.py:394-423 -> similarities [1, P]."""
     n_V, rows, in_f = weight3.shape

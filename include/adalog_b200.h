@@ -183,6 +183,15 @@ typedef struct {
 int adalog_fused_cand_gemm_err_grid(const adalog_fused_args* a);
 int adalog_fused_cand_gemm_err(const adalog_fused_args* a, void* stream);
 
+/* ---------------------------------------------------------------- fake-quant INFERENCE forward of a linear layer
+ * replaces: F.linear(Q_a(x), Q_w(W), b) of quant_layers/linear.py:46-51 / :90-92 (quant_forward).
+ * Same kernel, pipeline and argument block as adalog_cand_gemm_err, but the 128 rows of a unit are 128 consecutive
+ * TOKENS (A [m_rows, ka] = integer part of Q_a(x), a_rows = m_rows, U = UG = ceil(m_rows/128)), Bm [N, ka] the integer
+ * part of Q_w(W), and the epilogue writes  out[m, n] = rs[p] * cs[n] * D[m, n] + cb[n]  (rs = activation scale,
+ * cs = per-row weight scales, cb = bias with any shift term folded in) instead of accumulating an error.
+ * y, rb, partial are ignored. */
+int adalog_gemm_dequant(const adalog_gemm_err_args* a, float* out, int64_t ldo, int64_t m_rows, void* stream);
+
 /* plain (non-candidate) debug GEMM through the same tcgen05 pipeline: D[m,n] FP32 for A [128,ka], Bm [N,ka];
  * used by the tests to validate descriptors / swizzle / TMEM addressing in isolation. */
 int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, int dtype, void* stream);

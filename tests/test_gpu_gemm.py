@@ -366,3 +366,52 @@ def test_fused_int8_operands():
         out[i8] = sweep._run_fused(ctx.A2d, Kd, fixed, S2, U, S1, ctx.y2d, S2, rs, H, nl, 128, i8=i8, cs=c2, cz=z2,
                                    pstride=c2.shape[1], gstride=1, g_div=S1, g_mod=H)
     assert torch.allclose(out[True], out[False], rtol=1e-9, atol=0), (out[True] - out[False]).abs().max().item()
+
+
+@pytest.mark.parametrize('case', ['w4a4', 'w3a3', 'w6a6', 'w8a8', 'log4', 'log3_reparamed', 'nobias_ragged'])
+def test_tensor_core_inference_forward(case, monkeypatch):
+    """quant_forward through adalog_gemm_dequant (exact integer GEMM + dequantising epilogue) against the reference's
+    composition F.linear(Q_a(x), Q_w(W), b) in FP32: same values to FP32 rounding (the integer path is the exact one)."""
+    from adalog_b200.quant_layers import linear as L
+    torch.manual_seed(7)
+    log = case.startswith('log')
+    bits = {'w4a4': 4, 'w3a3': 3, 'w6a6': 6, 'w8a8': 8, 'log4': 4, 'log3_reparamed': 3, 'nobias_ragged': 4}[case]
+    in_f, out_f, ntok = (200, 72, 333) if case == 'nobias_ragged' else (384, 1152, 788)
+    if log:
+        in_f, out_f = 1536, 384
+        m = L.PostGeluLogBasedBatchingQuantLinear(in_f, out_f, w_bit=bits, a_bit=bits, n_V=1, eq_n=128, fpcs=True, steps=6)
+    else:
+        m = L.AsymmetricallyBatchingQuantLinear(in_f, out_f, bias=case != 'nobias_ragged', w_bit=bits, a_bit=bits,
+                                                n_V=3 if out_f % 3 == 0 else 1, eq_n=128, fpcs=True, steps=6)
+    m = m.to(DEV)
+    x = torch.randn(4, ntok // 4 if ntok % 4 == 0 else ntok, in_f, device=DEV)
+    if log:
+        x = torch.nn.functional.gelu(x)
+    nl = 2 ** (bits - 1)
+    W3 = m.weight.data.view(m.n_V, m.crb_rows, in_f)
+    wmax, wmin = W3.amax(-1, keepdim=True), W3.amin(-1, keepdim=True)
+    m.w_quantizer.scale = torch.nn.Parameter((wmax - wmin) / (2 * nl - 1))
+    m.w_quantizer.zero_point = torch.nn.Parameter((-wmin / m.w_quantizer.scale.data).round())
+    m.w_quantizer.inited = True
+    if log:
+        m.a_quantizer.scale = torch.nn.Parameter(torch.tensor([float(x.max()) + L.GELU_MIN], device=DEV))
+        m.a_quantizer.q.fill_(23)
+        m.a_quantizer.update_table()
+        if case == 'log3_reparamed':
+            m.a_quantizer.bias_reparamed.fill_(True)
+    else:
+        m.a_quantizer.scale = torch.nn.Parameter(((x.max() - x.min()) / (2 * nl - 1)).reshape(1))
+        m.a_quantizer.zero_point = torch.nn.Parameter((-x.min() / m.a_quantizer.scale.data).round().reshape(1))
+    m.a_quantizer.inited = True
+    m.calibrated = True
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        monkeypatch.setattr(L, 'TC_FORWARD', True)
+        y_tc = m(x)
+        assert '_tc_cache' in m.__dict__ and m.__dict__['_tc_cache'].get('key') is not None, 'tensor-core path not taken'
+        y_tc2 = m(x)                                   # cached weight operand
+        monkeypatch.setattr(L, 'TC_FORWARD', False)
+        y_ref = m(x)
+    assert torch.equal(y_tc, y_tc2)
+    scale = y_ref.abs().max().item()
+    assert (y_tc - y_ref).abs().max().item() <= 2e-5 * scale, ((y_tc - y_ref).abs().max().item(), scale)
