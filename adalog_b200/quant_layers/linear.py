@@ -23,7 +23,10 @@ __all__ = ['MinMaxQuantLinear', 'PTQSLQuantLinear', 'PTQSLBatchingQuantLinear', 
            'AsymmetricallyChannelWiseBatchingQuantLinear', 'PostGeluTwinUniformBatchingQuantLinear',
            'PostGeluLogBasedBatchingQuantLinear']
 
-TC_FORWARD = os.environ.get('ADALOG_B200_TC_FORWARD', '1') == '1'   # tensor-core inference forward (see quant_forward)
+# tensor-core inference forward (see PTQSLQuantLinear.quant_forward): opt-in, because the default forward is bit-identical
+# to the reference's F.linear(Q_a(x), Q_w(W), b) and calibration of later layers consumes it; enable per model with
+# utils.wrap_net.set_tensor_core_forward(model, True) or globally with ADALOG_B200_TC_FORWARD=1
+TC_FORWARD = os.environ.get('ADALOG_B200_TC_FORWARD', '0') == '1'
 GELU_MIN = 0.16997124254703522     # -min GELU(x); the post-GELU shift (reference linear.py:749)
 
 
@@ -98,13 +101,15 @@ class PTQSLQuantLinear(MinMaxQuantLinear):
         return w_sim, self.bias if self.bias is not None else None
 
     def quant_forward(self, x):
-        """reference linear.py:46-51 with :90-92.  Inference (no grad, quantizers not in training_mode, CUDA): one exact
-        integer GEMM on the tensor cores with the dequantisation in its epilogue (sweep.linear_quant_forward; the
-        weight operand is cached until the weight or its quantizer changes).  Anything else -- BRECQ's STE training
-        branches, per-channel activation quantizers before reparam, the PTQ4ViT twin quantizer -- takes the
-        reference's own composition of fake-quant tensors and F.linear."""
+        """reference linear.py:46-51 with :90-92: F.linear(Q_a(x), Q_w(W), b), bit-identical to the reference's
+        composition (the quantizers are the sm_100a kernels, the product is FP32).  With `tc_forward` enabled
+        (set_tensor_core_forward / ADALOG_B200_TC_FORWARD=1; inference only: no grad, no training_mode) the same
+        product is ONE exact integer GEMM on the tensor cores with the dequantisation in its epilogue
+        (sweep.linear_quant_forward; weight operand cached until the weight or its quantizer changes): equal to the
+        FP32 composition to FP32 rounding (<= 2e-5 of the output range, tests/test_gpu_gemm.py), not bit for bit."""
         assert self.calibrated, f"Module should be calibrated before run quant_forward for {self}"
-        if (TC_FORWARD and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+        tc = self.__dict__.get('tc_forward')
+        if ((TC_FORWARD if tc is None else tc) and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
                 and not self.w_quantizer.training_mode and not self.a_quantizer.training_mode
                 and self.w_quantizer.n_bits < 32 and self.a_quantizer.n_bits < 32):
             cache = self.__dict__.setdefault('_tc_cache', {})

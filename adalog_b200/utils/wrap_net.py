@@ -156,3 +156,15 @@ def wrap_reparamed_modules_in_net(model):
         new.to(module.weight.device)
         setattr(parent, leaf, new)
     return model
+
+
+def set_tensor_core_forward(model, enabled=True):
+    """Switch the linear layers' `quant_forward` between the default (bit-identical to the reference's
+    F.linear(Q_a(x), Q_w(W), b)) and the exact-integer tensor-core GEMM with a dequantising epilogue
+    (quant_layers/linear.py: PTQSLQuantLinear.quant_forward).  For evaluation / serving after calibration."""
+    n = 0
+    for m in model.modules():
+        if hasattr(m, 'w_quantizer') and hasattr(m, 'in_features'):
+            m.tc_forward = bool(enabled)
+            n += 1
+    return n

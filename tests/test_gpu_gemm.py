@@ -406,11 +406,11 @@ def test_tensor_core_inference_forward(case, monkeypatch):
     m.calibrated = True
     m.mode = 'quant_forward'
     with torch.no_grad():
-        monkeypatch.setattr(L, 'TC_FORWARD', True)
+        m.tc_forward = True
         y_tc = m(x)
         assert '_tc_cache' in m.__dict__ and m.__dict__['_tc_cache'].get('key') is not None, 'tensor-core path not taken'
         y_tc2 = m(x)                                   # cached weight operand
-        monkeypatch.setattr(L, 'TC_FORWARD', False)
+        m.tc_forward = False
         y_ref = m(x)
     assert torch.equal(y_tc, y_tc2)
     scale = y_ref.abs().max().item()
