@@ -41,3 +41,18 @@ with torch.no_grad():
     model(images[:32])
 for r in rows[:12] + rows[-3:]:
     print(r)
+
+# sensitivity of the network itself: the DEFAULT forward on inputs perturbed at the 1e-7 level vs unperturbed
+for h in hs:
+    h.remove()
+from adalog_b200.utils.wrap_net import set_tensor_core_forward  # noqa: E402
+with torch.no_grad():
+    ref = model(images[:n_img])
+    pert = model(images[:n_img] * (1 + 1e-7 * torch.randn_like(images[:n_img])))
+    set_tensor_core_forward(model, True)
+    tc = model(images[:n_img])
+    set_tensor_core_forward(model, False)
+agree = lambda a, b: float((a.argmax(-1) == b.argmax(-1)).float().mean())
+rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+print(f'default vs default on 1e-7-perturbed images: top-1 agreement {agree(pert, ref):.3f}, max rel logit diff {rel(pert, ref):.3f}')
+print(f'tensor-core vs default, same images:          top-1 agreement {agree(tc, ref):.3f}, max rel logit diff {rel(tc, ref):.3f}')
