@@ -525,3 +525,4 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         w_sim, bias_sim = self.quant_weight_bias()
         self.bias.data.copy_(bias_sim + (x_ @ w_sim.transpose(0, 1)).squeeze())
         self.a_quantizer.bias_reparamed.data.copy_(torch.tensor(True))
+        self.a_quantizer.bias_reparamed._adalog_flag = None      # (.data writes do not bump the version counter)

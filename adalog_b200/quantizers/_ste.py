@@ -12,3 +12,22 @@ def floor_ste(x: torch.Tensor):
 
 def ceil_ste(x: torch.Tensor):
     return (x.ceil() - x).detach() + x
+
+
+def flag(t):
+    """bool(t) for a 0-d flag buffer (e.g. `bias_reparamed`) without a device synchronisation on every inference
+    forward: under no_grad the value is read once and remembered on the tensor until it is modified in place or moved
+    (writes through `.data` do not bump the version counter: reparam_bias() invalidates explicitly).  With autograd
+    enabled (BRECQ training drives these modules) the tensor is always read."""
+    if torch.is_grad_enabled():
+        return bool(t)
+    key = (t.data_ptr(), t._version)
+    hit = getattr(t, '_adalog_flag', None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    v = bool(t)
+    try:
+        t._adalog_flag = (key, v)
+    except AttributeError:
+        pass
+    return v

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._ste import round_ste
+from ._ste import flag, round_ste
 
 __all__ = ['Log2Quantizer', 'LogSqrt2Quantizer', 'AdaLogQuantizer', 'ShiftLog2Quantizer', 'ShiftLogSqrt2Quantizer',
            'ShiftAdaLogQuantizer']
@@ -131,7 +131,7 @@ class _ShiftMixin:
         self.register_buffer('bias_reparamed', torch.tensor(False))
 
     def forward(self, x):
-        return self._forward(x, self.shift, not bool(self.bias_reparamed))
+        return self._forward(x, self.shift, not flag(self.bias_reparamed))
 
     def codes(self, x):
         return self._kernel(x, self.shift, False, want_codes=True)[1]

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._ste import round_ste
+from ._ste import flag, round_ste
 
 __all__ = ['UniformQuantizer', 'ShiftUniformQuantizer', 'TwinUniformQuantizer']
 
@@ -64,7 +64,7 @@ class ShiftUniformQuantizer(UniformQuantizer):
 
     def forward(self, x):
         result = UniformQuantizer.forward(self, x + self.shift)
-        return result if self.bias_reparamed else result - self.shift
+        return result if flag(self.bias_reparamed) else result - self.shift
 
 
 class TwinUniformQuantizer(UniformQuantizer):

@@ -16,6 +16,7 @@ import os
 import torch
 
 from . import ops
+from .quantizers._ste import flag as _flag
 from .utils import dist as adist
 
 WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '2048')) << 20
@@ -339,7 +340,7 @@ def linear_quant_forward(x2d, weight3, bias, wq, aq, cache=None):
         m2 = torch.round(_f32(aq.table2) * (4 * nl - 2))
         A = ops.gen_log_fixed(x2d, aq.scale, aq.q, aq.shift, aq.table1, m2, nl)
         a_scale = _f32(aq.scale).double().reshape(1) / (4 * nl - 2)
-        if not bool(getattr(aq, 'bias_reparamed', False)):
+        if not _flag(aq.bias_reparamed):
             b = (b.double() - _f32(aq.shift).double().reshape(1) * s_w.double() * colsum.double()).float()
     else:
         s_a, z_a = uniform_operand_params(aq)
