@@ -37,13 +37,13 @@ namespace fused {
 
 constexpr int kMaxBN = 256;
 constexpr int kMaxKB = 4;               // K blocks of 128 bytes: K <= 256 (bf16) / 512 (int8)
-constexpr int kAccStages = 2;
+constexpr int kAccStages = 8;            // TMEM accumulator stages: 512 columns / (BN rounded up to 64, 128 or 256)
 constexpr uint32_t kTmemCols = 512;
 constexpr int kEpiWarp0 = 2;
 constexpr int kMaxEpiWarps = 8;         // 4 or 8 epilogue warps (one or two column groups), the other workers produce:
 constexpr int kWorkWarps = 14;          // the split follows the shape (PV: N = 64, K = 197 wants 4 + 10; QK^T 8 + 6)
 constexpr int kThreads = (kEpiWarp0 + kWorkWarps) * 32;    // 512 threads x 128 registers = the whole register file
-constexpr int kMaxStages = 2;                              // candidate-tile stages
+constexpr int kMaxStages = 4;                              // candidate-tile stages (as many as fit in shared memory)
 constexpr int kSlabsPerGroup = kMaxBN / 32;                // slabs one epilogue warp may handle (one column group)
 constexpr uint32_t kABlock = kBM * 128;                    // bytes of one K block of the candidate tile (16 KiB)
 
@@ -64,7 +64,7 @@ struct FArgs {
   const float* cs; const float* cz; long long pstride, gstride, g_div, g_mod;
   const long long* cq; const float* mtab;
   int P, nl;
-  int KB, N, BN, U, UG, cpg, nst, epi_warps, dbg;
+  int KB, N, BN, U, UG, cpg, nst, nacc, acc_cols, epi_warps, dbg;
   long long brpg, g_base, u_base;
   const float* y; long long ldy;
   const float* rs; long long rs_div, rs_mod;
@@ -171,12 +171,12 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       const uint32_t blk = (uint32_t)a.BN * 128u;
       FWAIT(&tl.bfull, 0);
       for (int t = 0; t < n_units; ++t) {
-        const uint32_t as = t & 1, aphase = (t >> 1) & 1;
+        const uint32_t as = t % a.nacc, aphase = (t / a.nacc) & 1;
         const int st = t % a.nst;
         FWAIT(&tl.tempty[as], aphase ^ 1);
         FWAIT(&tl.afull[st], (t / a.nst) & 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * kMaxBN;
+        const uint32_t tmem_d = tmem_base + as * a.acc_cols;
         for (int kb = 0; kb < a.KB; ++kb) {
           const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)(st * a.KB + kb) * kABlock));
           const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)kb * blk));
@@ -236,7 +236,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
     const int nslab = (a.N + 31) >> 5;
     if (n_units > 0) load_y(u0);
     for (int t = 0; t < n_units; ++t) {
-      const uint32_t as = t & 1, aphase = (t >> 1) & 1;
+      const uint32_t as = t % a.nacc, aphase = (t / a.nacc) & 1;
       __syncwarp();                      // every lane is done reading the previous unit's staging row
 #pragma unroll
       for (int i = 0; i < kSlabsPerGroup; ++i) ysw[i * 32 + lane] = yreg[i];
@@ -245,7 +245,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       FWAIT(&tl.tfull[as], aphase);
       tc_fence_after();
       acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.0f;
-      const uint32_t tbase = tmem_base + lane_base + as * kMaxBN;
+      const uint32_t tbase = tmem_base + lane_base + as * a.acc_cols;
       uint32_t da[32], db[32];
       if (eg < nslab) tmem_ld32(tbase + eg * 32, da);
       int l0 = 0;
@@ -440,8 +440,13 @@ static size_t smem_bytes(const adalog_fused_args* a, int nst) {
   return b;
 }
 constexpr size_t kSmemLimit = 227 * 1024 - sizeof(Tail);
-// two candidate-tile stages when they fit (the producers then run a unit ahead of the MMA), else one
-static int stages(const adalog_fused_args* a) { return smem_bytes(a, 2) <= kSmemLimit ? 2 : 1; }
+// as many candidate-tile stages as fit (<= 4): the producers then run units ahead of the MMA, which with up to 8
+// accumulator stages in TMEM turns the per-unit produce -> MMA -> epilogue hand-offs from a latency chain into queues
+static int stages(const adalog_fused_args* a) {
+  int n = 1;
+  while (n < kMaxStages && smem_bytes(a, n + 1) <= kSmemLimit) ++n;
+  return n;
+}
 
 static int validate(const adalog_fused_args* a, bool need_partial) {
   ADALOG_REQUIRE(a && a->x && a->Bm && a->y && a->rs, -1, "fused_cand_gemm_err: null pointer");
@@ -476,6 +481,8 @@ static int launch(const adalog_fused_args* a, cudaStream_t st) {
   k.cq = a->cq; k.mtab = a->mtab; k.P = a->P; k.nl = a->n_levels;
   k.KB = a->KB; k.N = a->N; k.BN = a->BN; k.U = a->U; k.UG = a->UG; k.cpg = (a->UG + a->upc - 1) / a->upc;
   k.nst = stages(a);
+  k.acc_cols = a->BN <= 64 ? 64 : (a->BN <= 128 ? 128 : 256);
+  k.nacc = (int)kTmemCols / k.acc_cols;
   k.epi_warps = a->epi_warps;
   { const char* e = getenv("ADALOG_B200_FUSED_DBG"); k.dbg = e ? atoi(e) : 0; }   // diagnostics: 1 = no generation, 2 = no epilogue math
   k.brpg = a->brpg; k.g_base = a->g_base; k.u_base = a->u_base;
