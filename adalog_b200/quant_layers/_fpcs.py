@@ -7,6 +7,8 @@ scoring itself is delegated to `score(scales, aux, topk) -> indices`, i.e. to th
 """
 import torch
 
+from ..utils import dist as adist
+
 
 def candidate_chunks(P, tile=128):
     """slices of at most `tile` candidates (the kernels score one TMEM-lane tile of 128 per pass)"""
@@ -71,21 +73,60 @@ def percentile_grid(delta_min, delta_max, n_levels, num_zp, num_scale, axis, lea
 
 def chunked_quantile(x2, pct):
     """quantile over the last dim of x2 = x.view(g, 1, -1), doubling the middle dim until the reduced dim fits
-    torch.quantile's 2^24 limit, then averaging the chunk quantiles (linear.py:465-471, matmul.py:223-230)."""
+    torch.quantile's 2^24 limit, then averaging the chunk quantiles (linear.py:465-471, matmul.py:223-230).
+
+    x2 is this rank's shard (all of x without data parallelism); the statistics are those of the concatenation of the
+    shards in rank order.  A chunk is either a whole number of ranks (exact distributed selection per group of ranks)
+    or a fraction of one rank's shard (local quantiles, the per-chunk values exchanged before the mean)."""
     g = x2.shape[0]
+    R = adist.world_size()
+    n_loc = x2.numel() // g
     mbs = 1
-    while x2.numel() // (g * mbs) > (1 << 24):
+    while (n_loc * R) // mbs > (1 << 24):
         mbs *= 2
-    x2 = x2.reshape(g, mbs, -1)
-    up, lo = quantile_pair(x2, pct, -1)
+    if R == 1 or mbs >= R:
+        if mbs % R:
+            raise NotImplementedError(f'2^24 chunk rule with {mbs} chunks over {R} ranks')
+        up, lo = quantile_pair(x2.reshape(g, mbs // R, -1), pct, -1, local=True)      # [2, g, mbs/R]
+        up, lo = adist.all_gather_cat(up.contiguous(), dim=-1), adist.all_gather_cat(lo.contiguous(), dim=-1)
+    else:
+        if R % mbs:
+            raise NotImplementedError(f'2^24 chunk rule with {mbs} chunks over {R} ranks')
+        up, lo = quantile_pair(x2.reshape(g, 1, -1), pct, -1, seg=(adist.rank() // (R // mbs), mbs))   # [2, g, mbs]
     return up.mean(dim=-1), lo.mean(dim=-1)        # each [2, g]
 
 
-def quantile_pair(x, pct, dim):
+def quantile_pair(x, pct, dim, local=False, seg=None):
     """(quantile(x, pct), quantile(x, 1 - pct)) along dim with ONE sort: torch.quantile sorts once per call and
     interpolates every requested q independently, so the values are bit-identical to the reference's two calls
-    (linear.py:441-442, :459-471; matmul.py:223-230; conv.py:280-281)."""
+    (linear.py:441-442, :459-471; matmul.py:223-230; conv.py:280-281).
+
+    Under data parallelism (and unless local=True) `dim` is the sharded dimension: every rank sorts its own shard and
+    the two neighbouring order statistics of each q are selected exactly across ranks (utils/dist.py kth_values), then
+    interpolated with torch.quantile's own arithmetic (ranks = q*(n-1) in FP32, lerp): same bits as torch.quantile on
+    the all-gathered tensor.  seg=(my_segment, n_segments): statistics per group of ranks, returned with a trailing
+    segment axis [nq, ..., n_segments]."""
     n = pct.numel()
     q = torch.cat([pct, 1 - pct]).to(x.device)
-    both = torch.quantile(x, q, dim=dim)
-    return both[:n], both[n:]
+    if local or not adist.active():
+        both = torch.quantile(x, q, dim=dim)
+        return both[:n], both[n:]
+    xs = x.movedim(dim, -1)
+    lead = xs.shape[:-1]
+    srt, _ = xs.reshape(-1, xs.shape[-1]).contiguous().sort(dim=-1)
+    ranks_per_seg = adist.world_size() // (seg[1] if seg is not None else 1)
+    n_glob = srt.shape[1] * ranks_per_seg
+    ranks = q.to(srt.dtype) * (n_glob - 1)                   # torch.quantile: q * last_index in the input dtype
+    below = ranks.to(torch.int64)
+    weights = ranks - below
+    above = ranks.ceil().to(torch.int64)
+    vals = adist.kth_values(srt, torch.cat([below, above]), seg)       # [rows, 2nq] or [n_seg, rows, 2nq]
+    nq = q.numel()
+    if seg is not None:
+        vals = vals.permute(2, 1, 0)                                    # [2nq, rows, n_seg]
+        res = vals[:nq].clone().lerp_(vals[nq:], weights.view(-1, 1, 1))
+        res = res.reshape(nq, *lead[:-1], seg[1]) if lead and lead[-1] == 1 else res.reshape(nq, *lead, seg[1])
+    else:
+        vals = vals.t()                                                 # [2nq, rows]
+        res = vals[:nq].clone().lerp_(vals[nq:], weights.view(-1, 1)).reshape(nq, *lead)
+    return res[:n], res[n:]

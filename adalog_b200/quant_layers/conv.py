@@ -154,7 +154,7 @@ class AsymmetricallyBatchingQuantConv2d(PTQSLBatchingQuantConv2d):
         num_scale = int(self.eq_n / num_zp)
         pct = torch.tensor([l, r])
         w2 = self._weight2()
-        up, lo = _fpcs.quantile_pair(w2, pct, -1)
+        up, lo = _fpcs.quantile_pair(w2, pct, -1, local=True)        # weights are replicated, not sharded
         up, lo = up.unsqueeze(-1), lo.unsqueeze(-1)
         return _fpcs.percentile_grid(up[0:1] - lo[0:1], up[1:] - lo[1:], nl, num_zp, num_scale, 0, 2)
 

@@ -238,7 +238,7 @@ class AsymmetricallyBatchingQuantLinear(PTQSLBatchingQuantLinear):
         num_scale = int(self.eq_n / num_zp)
         pct = torch.tensor([l, r])
         w3 = self._weight3()
-        up, lo = _fpcs.quantile_pair(w3, pct, -1)
+        up, lo = _fpcs.quantile_pair(w3, pct, -1, local=True)        # weights are replicated, not sharded
         up, lo = up.unsqueeze(-1), lo.unsqueeze(-1)
         return _fpcs.percentile_grid(up[0:1] - lo[0:1], up[1:] - lo[1:], nl, num_zp, num_scale, 0, 3)
 
@@ -253,7 +253,7 @@ class AsymmetricallyBatchingQuantLinear(PTQSLBatchingQuantLinear):
         key = (bool(self.a_quantizer.channel_wise), l, r)
         cache = self._ctx.__dict__.setdefault('_pct_cache', {})
         if key not in cache:
-            x = adist.all_gather_cat(self._ctx.x2d.view(self._ctx.n_samples, -1))
+            x = self._ctx.x2d                      # this rank's samples; the helpers select across ranks exactly
             if self.a_quantizer.channel_wise:
                 up, lo = _fpcs.quantile_pair(x.reshape(-1, self.in_features), pct, 0)
             else:
@@ -426,10 +426,27 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         result.masked_fill_(torch.isnan(result), 0)
         return result
 
+    @staticmethod
+    def _positive_percentile_dist(x_local, q):
+        """positive_percentile of the concatenation of all ranks' shards (1-D), without gathering them: global count of
+        positive entries, then the exact element of rank ceil(count*q)-1 among them (utils/dist.py kth_values)."""
+        pos = torch.where(x_local > 0, x_local, torch.full_like(x_local, float('inf')))
+        srt, _ = pos.sort()
+        counts = adist.all_reduce_sum((x_local > 0).sum().to(torch.int64).view(1)).float()
+        ranks = ((counts * q).ceil().long() - 1).clamp(min=0)
+        vals = adist.kth_values(srt.view(1, -1), ranks.view(-1)).view(-1)
+        return torch.where(torch.isinf(vals) | (counts <= 0), torch.zeros_like(vals), vals)
+
     def calculate_percentile_activation_candidates(self, l=0.9, r=1.0):
         """reference linear.py:800-814"""
-        x = adist.all_gather_cat(self._ctx.x2d.view(self._ctx.n_samples, -1)).reshape(-1)
-        cand = self.positive_percentile(x, torch.tensor([l, r]).to(x.device)) + self.a_quantizer.shift.item()
+        # the calibration input does not change between search rounds: one sort per module
+        cache = self._ctx.__dict__.setdefault('_pct_cache', {})
+        if ('pos', l, r) not in cache:
+            x = self._ctx.x2d.reshape(-1)
+            q = torch.tensor([l, r]).to(x.device)
+            cache[('pos', l, r)] = (self._positive_percentile_dist(x, q) if adist.active()
+                                    else self.positive_percentile(x, q))
+        cand = cache[('pos', l, r)] + self.a_quantizer.shift.item()
         cand = cand.unsqueeze(0)
         ramp = torch.tensor([i / (self.eq_n - 1) for i in range(self.eq_n)]).to(x.device).view(1, -1)
         return cand, cand[:, 0:1] + (cand[:, 1:] - cand[:, 0:1]) * ramp

@@ -143,12 +143,11 @@ class AsymmetricallyBatchingQuantMatMul(PTQSLBatchingQuantMatMul):
         cache = self.__dict__.setdefault('_pct_cache', {})
         if key not in cache:
             cache.clear()
-            xg = adist.all_gather_cat(x)
-            if self.head_channel_wise:
-                x_ = xg.transpose(0, 1).contiguous()
+            if self.head_channel_wise:             # x: this rank's samples; chunked_quantile selects across ranks
+                x_ = x.transpose(0, 1).contiguous()
                 x_ = x_.view(x_.shape[0], 1, -1)
             else:
-                x_ = xg.reshape(1, 1, -1)
+                x_ = x.reshape(1, 1, -1)
             cache[key] = _fpcs.chunked_quantile(x_, pct)
         up, lo = cache[key]
         d_min = (up[0] - lo[0]).view(1, 1, -1, 1, 1)

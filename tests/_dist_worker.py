@@ -66,3 +66,53 @@ def worker(rank, world, port, kind, golden_path, out_dir):
     torch.save(sd, os.path.join(out_dir, f'rank{rank}.pt'))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def quantile_worker(rank, world, port, out_dir):
+    """distributed order statistics (utils/dist.py kth_values, _fpcs.quantile_pair / chunked_quantile, post-GELU
+    positive percentile) on this rank's shard of seeded data; rank 0 saves the results"""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from adalog_b200.quant_layers import _fpcs
+    from adalog_b200.quant_layers.linear import PostGeluLogBasedBatchingQuantLinear as PG
+    full = quantile_inputs()
+    pct = torch.tensor([0.9, 1.0])
+    out = {}
+    x = full['cw']                                            # [rows, C] sharded along rows
+    per = x.shape[0] // world
+    up, lo = _fpcs.quantile_pair(x[rank * per:(rank + 1) * per], pct, 0)
+    out['cw_up'], out['cw_lo'] = up, lo
+    h = full['heads']                                         # [B, H, S, D] sharded along B, per-head statistics
+    per = h.shape[0] // world
+    hl = h[rank * per:(rank + 1) * per].transpose(0, 1).contiguous()
+    out['head_up'], out['head_lo'] = _fpcs.chunked_quantile(hl.view(hl.shape[0], 1, -1), pct)
+    t = full['tensor']                                        # per-tensor, with a small 2^24 stand-in (see the test)
+    per = t.shape[0] // world
+    out['t_up'], out['t_lo'] = _fpcs.chunked_quantile(t[rank * per:(rank + 1) * per].reshape(1, 1, -1), pct)
+    g = full['gelu']
+    per = g.shape[0] // world
+    out['pos'] = PG._positive_percentile_dist(g[rank * per:(rank + 1) * per].reshape(-1), pct)
+    if rank == 0:
+        torch.save(out, os.path.join(out_dir, 'q.pt'))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def quantile_inputs():
+    gen = torch.Generator().manual_seed(123)
+    cw = torch.randn(8 * 50, 24, generator=gen) * torch.rand(24, generator=gen) * 3
+    cw[::7, 3] = 0.0
+    return {'cw': cw, 'heads': torch.randn(8, 3, 10, 6, generator=gen), 'tensor': torch.randn(8, 1000, generator=gen),
+            'gelu': torch.nn.functional.gelu(torch.randn(8, 500, generator=gen))}
+
+
+def quantile_worker_limit(rank, world, port, out_dir, limit):
+    """quantile_worker with the 2^24 reduced-dimension limit of torch.quantile replaced by `limit` in chunked_quantile,
+    so the three regimes of the chunk rule are reachable with small tensors"""
+    from adalog_b200.quant_layers import _fpcs
+    src = open(_fpcs.__file__).read().replace('(1 << 24)', f'({limit})')
+    body = 'def chunked_quantile' + src.split('def chunked_quantile')[1]
+    exec(compile(body, 'patched_fpcs', 'exec'), _fpcs.__dict__)
+    quantile_worker(rank, world, port, out_dir)

@@ -37,3 +37,32 @@ def test_two_ranks_match_single_process(kind, name, monkeypatch):
     for k in single:
         assert torch.equal(r0[k], r1[k]), f'{k}: ranks disagree'
         assert torch.equal(r0[k], single[k]), f'{k}: differs from the single-process result'
+
+
+@pytest.mark.parametrize('world,limit', [(2, 1 << 24), (4, 1 << 24), (2, 1000), (4, 4000), (4, 500)])
+def test_distributed_order_statistics_are_exact(world, limit, monkeypatch):
+    """Exact selection across ranks == torch.quantile / sort on the whole tensor, bit for bit: per-channel, per-head,
+    per-tensor with the 2^24 chunk rule (shrunk to `limit` so that a chunk is a fraction of a rank's shard, one rank,
+    or several ranks), and the post-GELU positive percentile."""
+    from adalog_b200.quant_layers import _fpcs
+    from adalog_b200.quant_layers.linear import PostGeluLogBasedBatchingQuantLinear as PG
+    src = open(_fpcs.__file__).read()
+    assert '(1 << 24)' in src
+    full = W.quantile_inputs()
+    pct = torch.tensor([0.9, 1.0])
+    # single-process reference with the same (possibly shrunk) chunk limit
+    mod = type(_fpcs)('fpcs_patched')
+    mod.__dict__.update(_fpcs.__dict__)
+    body = 'def chunked_quantile' + src.replace('(1 << 24)', f'({limit})').split('def chunked_quantile')[1]
+    exec(compile(body, 'patched_fpcs', 'exec'), mod.__dict__)
+    ref = {}
+    ref['cw_up'], ref['cw_lo'] = mod.quantile_pair(full['cw'], pct, 0)
+    h = full['heads'].transpose(0, 1).contiguous()
+    ref['head_up'], ref['head_lo'] = mod.chunked_quantile(h.view(h.shape[0], 1, -1), pct)
+    ref['t_up'], ref['t_lo'] = mod.chunked_quantile(full['tensor'].reshape(1, 1, -1), pct)
+    ref['pos'] = PG.positive_percentile(full['gelu'].reshape(-1), pct)
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(W.quantile_worker_limit, args=(world, free_port(), d, limit), nprocs=world, join=True)
+        got = torch.load(os.path.join(d, 'q.pt'))
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), (k, got[k], ref[k])
