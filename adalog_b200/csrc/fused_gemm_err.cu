@@ -26,11 +26,6 @@
 #include <type_traits>
 #include <stdlib.h>
 
-#ifdef ADALOG_FUSED_SPIN
-#define FWAIT mbar_wait_spin
-#else
-#define FWAIT mbar_wait
-#endif
 
 namespace adalog {
 namespace fused {
@@ -169,12 +164,12 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
     if (lane == 0 && n_units > 0) {
       const uint32_t idesc = I8 ? make_idesc_i8(a.BN) : make_idesc(a.BN);
       const uint32_t blk = (uint32_t)a.BN * 128u;
-      FWAIT(&tl.bfull, 0);
+      mbar_wait(&tl.bfull, 0);
       for (int t = 0; t < n_units; ++t) {
         const uint32_t as = t % a.nacc, aphase = (t / a.nacc) & 1;
         const int st = t % a.nst;
-        FWAIT(&tl.tempty[as], aphase ^ 1);
-        FWAIT(&tl.afull[st], (t / a.nst) & 1);
+        mbar_wait(&tl.tempty[as], aphase ^ 1);
+        mbar_wait(&tl.afull[st], (t / a.nst) & 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * a.acc_cols;
         for (int kb = 0; kb < a.KB; ++kb) {
@@ -242,7 +237,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       for (int i = 0; i < kSlabsPerGroup; ++i) ysw[i * 32 + lane] = yreg[i];
       __syncwarp();
       if (t + 1 < n_units) load_y(u0 + t + 1);   // consumed at the top of the next iteration
-      FWAIT(&tl.tfull[as], aphase);
+      mbar_wait(&tl.tfull[as], aphase);
       tc_fence_after();
       acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.0f;
       const uint32_t tbase = tmem_base + lane_base + as * a.acc_cols;
@@ -297,7 +292,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
 #pragma unroll
       for (int j = 0; j < EPT; ++j) xv[j] = xn[j];
       if (t + 1 < n_units) load_x(u0 + t + 1);
-      FWAIT(&tl.afree[st], ((t / a.nst) & 1) ^ 1);     // the MMAs that read this stage have retired
+      mbar_wait(&tl.afree[st], ((t / a.nst) & 1) ^ 1);     // the MMAs that read this stage have retired
       if (prod && !(a.dbg & 1)) {
         if (dead) {
           for (int p = cg; p < ADALOG_P; p += ncg) {
