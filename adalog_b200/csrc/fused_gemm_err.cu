@@ -131,6 +131,10 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       }
     }
   }
+  // the candidate-tile stages start as zeros: chunks beyond K are never written again
+  for (int i = threadIdx.x; i < a.nst * a.KB * (int)(kABlock / 16); i += kThreads)
+    reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -199,9 +203,11 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
     double acc64 = 0.0;
     float acc4[4];
     float yreg[kSlabsPerGroup];
+    const int my_slabs = max(0, (((a.N + 31) >> 5) - eg + G - 1) / G);     // slabs eg, eg+G, ... below N
     auto load_y = [&](int u) {
 #pragma unroll
       for (int i = 0; i < kSlabsPerGroup; ++i) {
+        if (i >= my_slabs) break;
         const int c = (eg + i * G) * 32 + lane;
         yreg[i] = (c < a.N) ? __ldg(a.y + (long long)u * a.ldy + c) : 0.0f;
       }
@@ -234,7 +240,10 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       const uint32_t as = t % a.nacc, aphase = (t / a.nacc) & 1;
       __syncwarp();                      // every lane is done reading the previous unit's staging row
 #pragma unroll
-      for (int i = 0; i < kSlabsPerGroup; ++i) ysw[i * 32 + lane] = yreg[i];
+      for (int i = 0; i < kSlabsPerGroup; ++i) {
+        if (i >= my_slabs) break;
+        ysw[i * 32 + lane] = yreg[i];
+      }
       __syncwarp();
       if (t + 1 < n_units) load_y(u0 + t + 1);   // consumed at the top of the next iteration
       mbar_wait(&tl.tfull[as], aphase);
@@ -268,12 +277,11 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
     // ===================== producers: the unit's 128 x K candidate tile, straight into swizzled smem =====================
     // thread -> one 16-byte chunk of the row (ch) for candidates cg, cg + ncg, ...
     const int w = threadIdx.x - kProdWarp0 * 32;
-    const int cpr = a.KB * 8;
-    const int ncg = kProdThreads / cpr;
+    const int cpr = (a.K + EPT - 1) / EPT;                    // chunks that hold real K elements (the padding chunks of
+    const int ncg = kProdThreads / cpr;                       // every stage were zeroed once, before the loop)
     const int ch = w % cpr, cg = w / cpr;
     const bool prod = cg < ncg;
     const int kc = ch * EPT;
-    const bool dead = kc >= a.K;                              // chunk entirely in the K padding: zeros
     const bool tail = kc + EPT > a.K;
     const uint32_t c_in = (uint32_t)(ch & 7);
     const int lw = 2 * a.nl + 1;
@@ -294,12 +302,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       if (t + 1 < n_units) load_x(u0 + t + 1);
       mbar_wait(&tl.afree[st], ((t / a.nst) & 1) ^ 1);     // the MMAs that read this stage have retired
       if (prod && !(a.dbg & 1)) {
-        if (dead) {
-          for (int p = cg; p < ADALOG_P; p += ncg) {
-            const uint32_t addr = a_chunk + (uint32_t)p * 128u + ((c_in ^ ((uint32_t)p & 7u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
-          }
-        } else if (GEN == GEN_UNIFORM) {
+        if (GEN == GEN_UNIFORM) {
           int nan_flag = 0;
 #pragma unroll
           for (int j = 0; j < EPT; ++j) nan_flag |= (xv[j] != xv[j]) ? 1 : 0;
@@ -355,7 +358,9 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
             if (two) u_store(p2, tb);
           }
         } else {
-          // post-softmax AdaLog base search (matmul.py:337-342): c = rint(-log2(x) * 37 / q), no scale, no clamp
+          // post-softmax AdaLog base search (matmul.py:337-342): c = rint(-log2(x) * 37 / q), no scale, no clamp.
+          // (Every thread logs its own 8-element chunk; sharing one log2f per element through shared memory was
+          // measured slower -- 11.1 -> 13.2 ms on the Swin window shape -- because of the per-unit producer barrier.)
           float lx[EPT], e1[EPT];
           int bad = 0;
 #pragma unroll

@@ -304,7 +304,7 @@ def gemm_dequant(A, m_rows, Bm, ka, N, rs, cs, cb, upc, S, i8=False, split_fast=
     return out
 
 
-SMEM_LIMIT = 227 * 1024 - 9600   # dynamic shared memory the fused kernel may ask for (its static part is ~9 KB)
+SMEM_LIMIT = 227 * 1024 - 16384   # dynamic shared memory the fused kernel may ask for (its static part is ~15 KB)
 
 
 def fused_plan(K, N, i8, log, n_levels):

@@ -116,7 +116,7 @@ def perf_probe():
 def perf_matmul():
     from adalog_b200.quantizers import UniformQuantizer
     import adalog_oracle as O
-    Bn, H, T, dh = 128, 6, 197, 64
+    Bn, H, T, dh = (128, 6, 197, 64) if not os.environ.get('SWIN_SHAPE') else (64 * 64, 4, 49, 32)   # DeiT-S / Swin-B stage 1
     torch.manual_seed(0)
     q = torch.randn(Bn, H, T, dh, device=DEV)
     k = torch.randn(Bn, H, dh, T, device=DEV)
