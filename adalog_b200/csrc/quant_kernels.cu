@@ -550,7 +550,8 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
                                                               const long long* __restrict__ cq, int P,
                                                               const float* __restrict__ shift,
                                                               const float* __restrict__ mtab, int nl,
-                                                              uint16_t* __restrict__ out, int kpad, int tpc, uint32_t magic4) {
+                                                              uint16_t* __restrict__ out, int kpad, int tpc, uint32_t magic4,
+                                                              int64_t U) {
   extern __shared__ float lut[];           // [per][2n + 1]
   __shared__ float4 cand[ADALOG_P];        // {mul / 2n, off / 2n, lim, mul}
   __shared__ float candq[ADALOG_P];
@@ -558,7 +559,6 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
   __shared__ float cscale[ADALOG_P];
   __shared__ float mt[64];
   __shared__ float lim_min_s;
-  const int64_t u = blockIdx.x;
   const float sh = shift ? shift[0] : 0.0f;
   const int ncode_i = 2 * nl;
   const float ncode = (float)ncode_i;
@@ -612,11 +612,14 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
   const int lane_chunk = threadIdx.x % tpc, pg = threadIdx.x / tpc;
   const int64_t dstep = (int64_t)npg * kpad;
   const int iters = (per - pg + npg - 1) / npg;
-  const float* xrow = x + u * ldx;
   // shared address of lut[0][0] minus the magic-number offset: addr = bits(t + 1.5*2^23) * 4 + lut_bias (mod 2^32)
   // (magic4 = bits(1.5*2^23) * 4 mod 2^32 arrives as a kernel argument: as a literal, ptxas re-splits it out of the
   // row address and spends an extra add per element on it)
   const uint32_t lut_bias = (uint32_t)__cvta_generic_to_shared(lut) - magic4;
+  // the per-candidate constants and the value LUT above are built once per CTA and reused for all of its units
+  // (with one unit per CTA the 128 x (2n+1) LUT cost as much as 29% of a 6-bit, K=512 unit)
+  for (int64_t u = blockIdx.x; u < U; u += gridDim.x) {
+  const float* xrow = x + u * ldx;
   for (int ch = lane_chunk; ch < cpr; ch += tpc) {
     const int kc = ch << 3;
     const bool tail = kc + 8 > K;
@@ -666,6 +669,7 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
       }
       store8(dst, v);
     }
+  }
   }
 }
 
@@ -897,7 +901,7 @@ int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const flo
   const int cpr = kpad / 8;
   const int tpc = cpr < 256 ? cpr : 256;
   const int npg = 256 / tpc;
-  dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
+  dim3 grid((unsigned)(U < (int64_t)kNumSMs * 8 ? U : (int64_t)kNumSMs * 8), (unsigned)cand_split(U, npg));
   cudaStream_t st = (cudaStream_t)stream;
   ADALOG_REQUIRE(2 * n_levels <= 64, -2, "gen_log_cand: AdaLog sweeps support n_bits <= 6 (bf16-exact numerators)");
   const size_t lut_bytes = (size_t)(ADALOG_P / grid.y) * (2 * n_levels + 1) * sizeof(float);
@@ -907,10 +911,10 @@ int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const flo
                        cudaSharedmemCarveoutMaxShared);
   if (cs)
     gen_log_cand_lut_kernel<true><<<grid, tpc * npg, lut_bytes, st>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
-                                                                      out, kpad, tpc, 0x2D000000u);
+                                                                      out, kpad, tpc, 0x2D000000u, U);
   else
     gen_log_cand_lut_kernel<false><<<grid, tpc * npg, lut_bytes, st>>>(x, K, ldx, cs, cq, P, shift, mtab, n_levels,
-                                                                       out, kpad, tpc, 0x2D000000u);
+                                                                       out, kpad, tpc, 0x2D000000u, U);
   return check_launch("gen_log_cand");
 }
 
