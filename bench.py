@@ -334,7 +334,7 @@ def run_ours(args):
                    for k, v in gemm_split.items()}
         out = dict(metric='fpcs_candidates_per_s', value=value, unit='candidates/s', n_gpus=world, steps=args.steps,
                    warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
-                   dtype='bf16 operands (exact integers) / f32 accumulate / f64 error sums', data='synthetic',
+                   dtype='int8 + bf16 operands holding exact integers (s32 / f32 accumulate), f64 error sums', data='synthetic',
                    config=workload_config(args), evaluations_per_step=evals, candidates_per_step=cands,
                    calibration_wall_s=ms_step / 1e3, fakequant_img_per_s=fq_img_s, fakequant_forward=fq_extra,
                    gpu_launches=launches, clocks=clocks,
