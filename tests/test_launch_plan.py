@@ -1,0 +1,56 @@
+"""CPU: invariants of the static launch plans (pure host logic, no kernel call).  A wrong plan would not crash -- the
+kernel validates and the partition is computed from (UG, cpg, S) on the device -- but it could leave SMs idle or break
+the 1024-column limit of the column-scale staging, so the planners are pinned here."""
+import math
+
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from adalog_b200 import ops, sweep
+
+
+@settings(max_examples=300, deadline=None)
+@given(nu=st.integers(1, 30000), NT=st.integers(1, 99), ka=st.sampled_from([64, 128, 384, 768, 1536, 3072]),
+       N=st.sampled_from([64, 197, 384, 768, 1152, 3072, 25216]), i8=st.booleans(), cs=st.booleans())
+def test_linear_launch_plan_invariants(nu, NT, ka, N, i8, cs):
+    BN = ops.pick_bn(N)
+    NT = (N + BN - 1) // BN
+    esz = 1 if i8 else 2
+    max_tps = (1024 // BN) if cs else 1 << 30
+    groups, upc, cpg, S, sf = sweep._launch_plan(nu, nu, NT, N * ka * esz, 128 * ka * esz,
+                                                 max((ka // 64) * BN * (1 if i8 else 2), 8 * BN), max_tps)
+    assert groups == 1 and 1 <= upc <= nu and cpg == math.ceil(nu / upc) and 1 <= S <= NT
+    assert math.ceil(NT / S) <= max_tps                       # a CTA never covers more than 1024 staged columns
+    # every unit and every N tile is covered exactly once by the device-side partition
+    units = [(ci * nu) // cpg for ci in range(cpg + 1)]
+    assert units[0] == 0 and units[-1] == nu and all(b >= a for a, b in zip(units, units[1:]))
+    assert max(b - a for a, b in zip(units, units[1:])) <= upc
+    tiles = [(y * NT) // S for y in range(S + 1)]
+    assert tiles[0] == 0 and tiles[-1] == NT and all(b > a for a, b in zip(tiles, tiles[1:]))
+    # L2 rule: when 148 units of candidate rows cannot sit in L2 the split-fast order is used
+    assert sf == (NT > 1 and 128 * ka * esz * min(sweep.NUM_SMS, nu) > sweep.L2_CAND_BYTES)
+
+
+@pytest.mark.parametrize('K,N,i8,log,nl,ok', [
+    (64, 197, False, False, 4, True), (197, 64, False, True, 4, True), (197, 197, False, False, 8, True),
+    (32, 49, False, False, 32, True), (49, 32, False, True, 32, True), (144, 144, False, False, 8, True),
+    (257, 64, False, False, 8, False),        # K > 4 blocks of 64
+    (64, 300, False, False, 8, False),        # more than one N tile
+    (197, 64, True, True, 4, False),          # AdaLog candidates are bf16
+    (197, 64, False, True, 64, False),        # 7-bit AdaLog is not bf16-exact
+])
+def test_fused_plan_eligibility(K, N, i8, log, nl, ok):
+    plan = ops.fused_plan(K, N, i8, log, nl)
+    assert (plan is not None) == ok
+    if ok:
+        KB, BN = plan
+        assert KB == math.ceil(K / (128 if i8 else 64)) <= 4 and N <= BN <= 256 and BN % 16 == 0
+
+
+@settings(max_examples=200, deadline=None)
+@given(groups=st.integers(1, 20000), ug=st.integers(1, 400), K=st.integers(8, 256), N=st.integers(8, 256))
+def test_fused_units_per_cta(groups, ug, K, N):
+    upc = sweep._fused_upc(groups, ug, K, N)
+    assert 1 <= upc <= ug
+    cpg = math.ceil(ug / upc)
+    assert cpg <= 16                                           # a CTA amortises its fixed-operand load over >= ug/16 units
