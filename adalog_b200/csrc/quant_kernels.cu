@@ -316,49 +316,71 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
                                                               const float* __restrict__ cs,
                                                               const float* __restrict__ cz, int P, int nl,
                                                               double* __restrict__ partial, int nsplit) {
+  // FP64 accumulators live in shared memory ([candidate][thread]: conflict free) so that the registers hold the four
+  // per-candidate constants of the FMA-pipe fast path (uq_code_fast, quant_device.cuh) for 16 candidates
+  __shared__ double acc_s[16][256];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int p0 = threadIdx.y * 16;
   const bool col_ok = c < Cw;
-  float s[16], z[16], r[16];
-  double acc[16];
+  const float L = (float)(2 * nl - 1);
+  const float two_n = (float)(2 * nl), inv2n = 1.0f / two_n;
+  float cx[16], cy[16], cw[16], s[16];
   float a32[16];
+  bool all_fast = nl > 0 && (nl & (nl - 1)) == 0;          // r/2n etc. are exact scalings only for a power of two
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    int p = min(p0 + j, P - 1);
-    int64_t ci = per_channel ? ((int64_t)min(c, Cw - 1) * P + p) : p;
+    const int p = min(p0 + j, P - 1);
+    const int64_t ci = per_channel ? ((int64_t)min(c, Cw - 1) * P + p) : p;
     s[j] = __ldg(cs + ci);
-    z[j] = __ldg(cz + ci);
-    r[j] = (z[j] == rintf(z[j])) ? __fdiv_rn(1.0f, s[j]) : __int_as_float(0x7fc00000);   // NaN: IEEE path only
-    acc[j] = 0.0;
+    const float z = __ldg(cz + ci);
+    const float r = __fdiv_rn(1.0f, s[j]);
+    all_fast = all_fast && z == rintf(z) && z >= 0.0f && z <= L && fabsf(r) <= 3.0e38f;
+    cx[j] = r * inv2n; cy[j] = z * inv2n; cw[j] = __fsub_rn(kMagic, z);
     a32[j] = 0.0f;
+    acc_s[j][tid] = 0.0;
   }
-  const float L = (float)(2 * nl - 1);
+  const float thr = all_fast ? kFracSafe : -1.0f;          // a thread with any irregular candidate always takes the IEEE path
+  const float Lq = L * inv2n;
   const int64_t M = (n_total + Cw - 1) / Cw;
   const int64_t rps = (M + nsplit - 1) / nsplit;
   const int64_t m0 = (int64_t)blockIdx.y * rps;
   const int64_t m1 = min(M, m0 + rps);
+  constexpr int RU = 4;                                    // rows per iteration: four independent loads in flight
   int cnt = 0;
-  for (int64_t m = m0; m < m1; ++m) {
-    const int64_t idx = m * Cw + c;
-    if (col_ok && idx < n_total) {
-      const float xv = __ldg(x + idx);
+  for (int64_t m = m0; m < m1; m += RU) {
+    float xv[RU];
+    bool ok[RU];
+#pragma unroll
+    for (int rr = 0; rr < RU; ++rr) {
+      const int64_t idx = (m + rr) * Cw + c;
+      ok[rr] = col_ok && m + rr < m1 && idx < n_total;
+      xv[rr] = ok[rr] ? __ldg(x + idx) : 0.0f;
+    }
+#pragma unroll
+    for (int rr = 0; rr < RU; ++rr) {
+      if (!ok[rr]) continue;
+      const float xr = xv[rr];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        bool unsafe = false;                              // exact fast path of the generators (same proof)
-        float qi = uq_int_fast(xv, make_float4(r[j], -z[j], L - z[j], s[j]), unsafe);
-        if (unsafe) qi = uq_int(xv, s[j], z[j], L);
-        float d = __fsub_rn(xv, __fmul_rn(qi, s[j]));
-        a32[j] = __fadd_rn(a32[j], __fmul_rn(d, d));
+        bool unsafe = false;                               // exact fast path of the generators (same proof)
+        const float tm = uq_code_fast(xr, make_float4(cx[j], cy[j], Lq, cw[j]), two_n, thr, unsafe);
+        float qi = __fsub_rn(tm, kMagic);                  // code - zp
+        if (unsafe) qi = uq_int(xr, s[j], __fsub_rn(kMagic, cw[j]), L);
+        const float d = __fsub_rn(xr, __fmul_rn(qi, s[j]));
+        a32[j] = fmaf(d, d, a32[j]);
       }
     }
-    if (++cnt == 32) {
+    cnt += RU;
+    if (cnt >= 32) {
       cnt = 0;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { acc[j] += (double)a32[j]; a32[j] = 0.0f; }
+      for (int j = 0; j < 16; ++j) { acc_s[j][tid] += (double)a32[j]; a32[j] = 0.0f; }
     }
   }
+  double acc[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] += (double)a32[j];
+  for (int j = 0; j < 16; ++j) acc[j] = acc_s[j][tid] + (double)a32[j];
   if (per_channel) {
     if (col_ok) {
 #pragma unroll
