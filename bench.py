@@ -305,12 +305,31 @@ def run_ours(args):
         return args.images_per_gpu / (e0.elapsed_time(e1) / 1e3), torch.cat(logits)
 
     fq_img_s, logits_ref = fq_rate(32)
+    # the same default forward replayed from a CUDA graph (batch 32 is launch-latency bound)
+    graphed_img_s, graphed_equal = None, None
+    try:
+        from adalog_b200.utils.graph import GraphedForward
+        gf = GraphedForward(model, dev_images[:32])
+        outs = []
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(0, args.images_per_gpu, 32):
+            outs.append(gf(dev_images[i:i + 32]).clone())
+        g1.record()
+        torch.cuda.synchronize()
+        graphed_img_s = args.images_per_gpu / (g0.elapsed_time(g1) / 1e3)
+        graphed_equal = bool(torch.equal(torch.cat(outs), logits_ref))
+        del gf
+    except Exception as e:                              # reported, never fatal for the calibration metric
+        graphed_equal = f'capture failed: {type(e).__name__}: {e}'[:200]
     fq_big, _ = fq_rate(args.images_per_gpu)
     set_tensor_core_forward(model, True)
     fq_tc, logits_tc = fq_rate(32)
     fq_tc_big, _ = fq_rate(args.images_per_gpu)
     set_tensor_core_forward(model, False)
-    fq_extra = dict(batch32_img_per_s=fq_img_s, full_batch_img_per_s=fq_big, tensor_core_batch32_img_per_s=fq_tc,
+    fq_extra = dict(batch32_img_per_s=fq_img_s, batch32_cuda_graph_img_per_s=graphed_img_s,
+                    batch32_cuda_graph_bit_identical=graphed_equal, full_batch_img_per_s=fq_big, tensor_core_batch32_img_per_s=fq_tc,
                     tensor_core_full_batch_img_per_s=fq_tc_big,
                     tensor_core_top1_agreement=float((logits_tc.argmax(-1) == logits_ref.argmax(-1)).float().mean()),
                     tensor_core_max_rel_logit_diff=float((logits_tc - logits_ref).abs().max() / logits_ref.abs().max()),
