@@ -638,8 +638,7 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
   // (magic4 = bits(1.5*2^23) * 4 mod 2^32 arrives as a kernel argument: as a literal, ptxas re-splits it out of the
   // row address and spends an extra add per element on it)
   const uint32_t lut_bias = (uint32_t)__cvta_generic_to_shared(lut) - magic4;
-  // the per-candidate constants and the value LUT above are built once per CTA and reused for all of its units
-  // (with one unit per CTA the 128 x (2n+1) LUT cost as much as 29% of a 6-bit, K=512 unit)
+  // (grid-stride over units; the host launches one CTA per unit, see adalog_gen_log_cand)
   for (int64_t u = blockIdx.x; u < U; u += gridDim.x) {
   const float* xrow = x + u * ldx;
   for (int ch = lane_chunk; ch < cpr; ch += tpc) {
@@ -923,7 +922,9 @@ int adalog_gen_log_cand(const float* x, int64_t U, int K, int64_t ldx, const flo
   const int cpr = kpad / 8;
   const int tpc = cpr < 256 ? cpr : 256;
   const int npg = 256 / tpc;
-  dim3 grid((unsigned)(U < (int64_t)kNumSMs * 8 ? U : (int64_t)kNumSMs * 8), (unsigned)cand_split(U, npg));
+  // one CTA per unit: capping the grid and looping over units (to build the LUT once per CTA) measured 2x slower --
+  // uneven unit counts per CTA and fewer CTAs to fill the SMs beside the GEMM -- so the kernel's unit loop runs once
+  dim3 grid((unsigned)U, (unsigned)cand_split(U, npg));
   cudaStream_t st = (cudaStream_t)stream;
   ADALOG_REQUIRE(2 * n_levels <= 64, -2, "gen_log_cand: AdaLog sweeps support n_bits <= 6 (bf16-exact numerators)");
   const size_t lut_bytes = (size_t)(ADALOG_P / grid.y) * (2 * n_levels + 1) * sizeof(float);
