@@ -34,3 +34,12 @@ def test_binding_covers_header():
 def test_struct_layout_matches_header():
     # adalog_gemm_err_args: 2 ptr + 2 i64 + 10 i32 + 3 i64 + ptr + i64 + 2 ptr + 2 i64 + 2 ptr + ptr
     assert ctypes.sizeof(_lib.GemmErrArgs) == 8 * 4 + 4 * 10 + 8 * 3 + 8 * 2 + 8 * 2 + 8 * 2 + 8 * 2 + 8
+
+
+def test_integration_stub_struct_matches_binding():
+    """the ctypes stub shown to reference maintainers in INTEGRATION.md lists the fields of adalog_gemm_err_args in the
+    same order as the tested binding"""
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = text[text.index('class _GemmErrArgs'):text.index('def _check')]
+    names = re.findall(r"\('(\w+)',\s*ctypes\.", block)
+    assert names == [f[0] for f in _lib.GemmErrArgs._fields_]
