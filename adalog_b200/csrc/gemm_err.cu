@@ -326,17 +326,29 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t da[32], db[32];
       if (eg < nslab) tmem_ld32(tbase + eg * 32, da);
       int l0 = 0;
+      // MODE_RB (W-side / conv sweeps): the columns are this rank's calibration tokens, so the FP32 partial is promoted
+      // to FP64 per 32-column slab.  Slabs sit at absolute multiples of 32 tokens (BN % 32 == 0 on this path), hence
+      // every FP32 rounding is the same however the tokens are sharded over GPUs (shards of a multiple of 32 tokens)
+      // or tiled; what remains order-dependent is FP64 addition of FP32-valued terms.  The other modes sum over the
+      // output features of whole units (tokens / rows), which no sharding splits: one promotion per tile.
+      constexpr bool SLAB64 = MODE == MODE_RB;
+      auto flush = [&]() {
+        acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+        acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.0f;
+      };
       for (int sl = eg; sl < nslab; sl += 2 * G, l0 += 64) {
         tmem_ld_wait();
         if (sl + G < nslab) tmem_ld32(tbase + (sl + G) * 32, db);
         consume(da, sl * 32, l0, toff + sl * 32, ncols - sl * 32, rs, rb, n0, ncols);
+        if (SLAB64) flush();
         if (sl + G < nslab) {
           tmem_ld_wait();
           if (sl + 2 * G < nslab) tmem_ld32(tbase + (sl + 2 * G) * 32, da);
           consume(db, (sl + G) * 32, l0 + 32, toff + (sl + G) * 32, ncols - (sl + G) * 32, rs, rb, n0, ncols);
+          if (SLAB64) flush();
         }
       }
-      acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+      if (!SLAB64) acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tempty[as]);
@@ -373,6 +385,8 @@ static int validate(const adalog_gemm_err_args* a, bool need_partial) {
   ADALOG_REQUIRE(a->a_rows >= (int64_t)a->U * kBM, -1, "cand_gemm_err: A has fewer than U*128 rows");
   ADALOG_REQUIRE(a->rs_div > 0 && a->rs_mod > 0 && a->rs, -1, "cand_gemm_err: row scale required");
   ADALOG_REQUIRE((a->cs == nullptr) == (a->cb == nullptr), -1, "cand_gemm_err: cs and cb come together");
+  ADALOG_REQUIRE(!a->rb || a->cs || a->BN % 32 == 0, -1,
+                 "cand_gemm_err: with a row bias (W-side sweeps) BN must be a multiple of 32 (per-slab FP64 promotion)");
   ADALOG_REQUIRE(a->y && (a->partial || !need_partial), -1, "cand_gemm_err: y / partial required");
   const int NT = (a->N + a->BN - 1) / a->BN;
   ADALOG_REQUIRE(a->S <= NT, -1, "cand_gemm_err: more N splits than N tiles");

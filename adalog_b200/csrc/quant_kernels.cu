@@ -343,7 +343,10 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
   const float thr = all_fast ? kFracSafe : -1.0f;          // a thread with any irregular candidate always takes the IEEE path
   const float Lq = L * inv2n;
   const int64_t M = (n_total + Cw - 1) / Cw;
-  const int64_t rps = (M + nsplit - 1) / nsplit;
+  // rows per split: a multiple of 32, so that the 32-row groups whose FP32 partial is promoted to FP64 sit at absolute
+  // multiples of 32 rows -- the FP32 roundings are then the same however the rows are split over CTAs or sharded over
+  // GPUs (shards of a multiple of 32 rows)
+  const int64_t rps = (((M + nsplit - 1) / nsplit + 31) / 32) * 32;
   const int64_t m0 = (int64_t)blockIdx.y * rps;
   const int64_t m1 = min(M, m0 + rps);
   constexpr int RU = 4;                                    // rows per iteration: four independent loads in flight

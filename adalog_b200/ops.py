@@ -5,11 +5,13 @@ No CPU path exists: CPU tensors raise AdalogError.
 """
 import ctypes
 import math
+import threading
 
 import torch
 
 from . import _lib
-from ._lib import AdalogError, FusedArgs, GemmErrArgs, call
+from ._lib import AdalogError, FusedArgs, GemmErrArgs
+from ._lib import call as _lib_call
 
 P_TILE = 128   # ADALOG_P
 BK = 64        # ADALOG_BK
@@ -36,10 +38,26 @@ def profile_gemm_summary(split=False):
     return tot(PROFILE['gemm'])
 
 
+_tls = threading.local()
+
+
 def _cuda(*ts):
+    """All operands of one kernel call must be CUDA tensors on ONE device; that device becomes the target of the call:
+    `call` below switches to it for the launch (TMA descriptors, kernel attributes and the launch itself are per-device
+    state) and `_stream()` hands the C ABI torch's current stream OF THAT DEVICE -- a model on cuda:1 while the current
+    device is 0 launches on cuda:1, not on device 0's stream with device-1 pointers."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise AdalogError('adalog_b200 kernels need CUDA tensors (there is no CPU fallback)')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise AdalogError(f'operands of one adalog_b200 call sit on different devices ({dev} and {t.device})')
+    _tls.dev = dev
+    return dev
 
 
 def _p(t):
@@ -47,7 +65,15 @@ def _p(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(getattr(_tls, 'dev', None)).cuda_stream)
+
+
+def call(name, *args):
+    dev = getattr(_tls, 'dev', None)
+    if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+        return _lib_call(name, *args)
+    with torch.cuda.device(dev):
+        return _lib_call(name, *args)
 
 
 def _f32(t):
@@ -208,6 +234,7 @@ def gen_uniform_fixed(x2d, scale_g, zp_g, g_div, g_mod, n_levels, want_rowsum=Fa
 def gen_uniform_cand(x2d, u0, nu, cs, cz, P, pstride, gstride, g_div, g_mod, n_levels, out, krep=1, rowsum=None,
                      i8=False):
     """rows [u0, u0+nu) of x2d -> out[(u*128+p), krep*kpad]  (bf16, or int8 when i8)."""
+    _cuda(x2d, cs, cz, out, rowsum)
     K = x2d.shape[1]
     xs = x2d[u0:u0 + nu]
     call('adalog_gen_uniform_cand', _p(xs), nu, K, x2d.stride(0), _p(cs), _p(cz), int(P), int(pstride), int(gstride),
@@ -216,6 +243,7 @@ def gen_uniform_cand(x2d, u0, nu, cs, cz, P, pstride, gstride, g_div, g_mod, n_l
 
 
 def gen_log_cand(x2d, u0, nu, cs, cq, P, shift, mtab, n_levels, out):
+    _cuda(x2d, cs, cq, shift, mtab, out)
     K = x2d.shape[1]
     xs = x2d[u0:u0 + nu]
     call('adalog_gen_log_cand', _p(xs), nu, K, x2d.stride(0), _p(cs), _p(cq), int(P), _p(shift), _p(mtab),
@@ -245,17 +273,20 @@ def gen_split3(x2d):
 
 
 # ------------------------------------------------------------------------------------------ candidate GEMM
-def pick_bn(N):
+def pick_bn(N, mult=16):
+    """N-tile width: as few tiles as possible, a multiple of `mult` (16 = the UMMA granule; 32 on the W-side / conv
+    sweeps, whose epilogue promotes one FP32 partial per absolute 32-token slab to FP64 -- see gemm_err.cu SLAB64)"""
     nt = (N + 255) // 256
-    bn = ((math.ceil(N / nt) + 15) // 16) * 16
-    return min(256, max(16, bn))
+    bn = ((math.ceil(N / nt) + mult - 1) // mult) * mult
+    return min(256, max(mult, bn))
 
 
 def cand_gemm_err(A, a_rows, Bm, ka, N, U, UG, brpg, g_base, u_base, y, y_off, ldy, rs, rb, rs_div, rs_mod, cs, cb,
                   upc, S, BN=None, k_true=None, i8=False, split_fast=False):
     """One launch of adalog_cand_gemm_err.  Returns FP64 partial [S, gridX, 128].  ka: operand pitch in elements.
     split_fast only changes which CTAs are co-resident (L2 reuse), never a result bit."""
-    BN = BN or pick_bn(N)
+    BN = BN or pick_bn(N, 32 if rb is not None else 16)
+    _cuda(A, Bm, y, rs, rb, cs, cb)
     a = GemmErrArgs()
     a.A, a.Bm = A.data_ptr(), Bm.data_ptr()
     a.a_rows, a.b_rows = int(a_rows), int(Bm.shape[0])

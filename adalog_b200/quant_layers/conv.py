@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 from .. import sweep
 from ..quantizers.uniform import UniformQuantizer
+from ..quantizers._ste import assign
 from . import _fpcs
 
 __all__ = ['MinMaxQuantConv2d', 'PTQSLQuantConv2d', 'PTQSLBatchingQuantConv2d', 'AsymmetricallyBatchingQuantConv2d']
@@ -142,8 +143,8 @@ class AsymmetricallyBatchingQuantConv2d(PTQSLBatchingQuantConv2d):
         _, best = torch.topk(sims, k=topk, dim=0)
         best = best.view(topk, -1, 1)
         if topk == 1:
-            self.w_quantizer.scale.data.copy_(torch.gather(weight_scale_candidates, dim=0, index=best).squeeze(dim=0))
-            self.w_quantizer.zero_point.data.copy_(
+            assign(self.w_quantizer.scale, torch.gather(weight_scale_candidates, dim=0, index=best).squeeze(dim=0))
+            assign(self.w_quantizer.zero_point, 
                 torch.gather(weight_zero_point_candidates, dim=0, index=best).squeeze(dim=0))
         return best
 
@@ -170,8 +171,8 @@ class AsymmetricallyBatchingQuantConv2d(PTQSLBatchingQuantConv2d):
                                       '(conv.py:329 uses an undefined name); qconv_a_bit must be >= 8')
         self._initialize_calib_parameters()
         cs, cz = self.calculate_percentile_weight_candidates()
-        self.w_quantizer.scale.data.copy_(cs[-2])
-        self.w_quantizer.zero_point.data.copy_(cz[-2])
+        assign(self.w_quantizer.scale, cs[-2])
+        assign(self.w_quantizer.zero_point, cz[-2])
         self.w_quantizer.inited = True
         if self.fpcs:
             self.weight_fpcs(steps=self.steps, search_strategy=AsymmetricallyBatchingQuantConv2d._search_best_w_scale)

@@ -17,6 +17,7 @@ from .. import sweep
 from ..quantizers.uniform import UniformQuantizer, TwinUniformQuantizer
 from ..quantizers.logarithm import ShiftAdaLogQuantizer, ShiftLog2Quantizer, ShiftLogSqrt2Quantizer
 from ..utils import dist as adist
+from ..quantizers._ste import assign
 from . import _fpcs
 
 __all__ = ['MinMaxQuantLinear', 'PTQSLQuantLinear', 'PTQSLBatchingQuantLinear', 'AsymmetricallyBatchingQuantLinear',
@@ -176,12 +177,12 @@ class AsymmetricallyBatchingQuantLinear(PTQSLBatchingQuantLinear):
         return parts[0] if len(parts) == 1 else torch.cat(parts, dim=axis)
 
     def _store_w(self, cs, cz, idx):
-        self.w_quantizer.scale.data.copy_(torch.gather(cs, dim=0, index=idx).squeeze(0))
-        self.w_quantizer.zero_point.data.copy_(torch.gather(cz, dim=0, index=idx).squeeze(0))
+        assign(self.w_quantizer.scale, torch.gather(cs, dim=0, index=idx).squeeze(0))
+        assign(self.w_quantizer.zero_point, torch.gather(cz, dim=0, index=idx).squeeze(0))
 
     def _store_a(self, cs, cz, idx):
-        self.a_quantizer.scale.data.copy_(torch.gather(cs, dim=-1, index=idx).squeeze(-1))
-        self.a_quantizer.zero_point.data.copy_(torch.gather(cz, dim=-1, index=idx).squeeze(-1))
+        assign(self.a_quantizer.scale, torch.gather(cs, dim=-1, index=idx).squeeze(-1))
+        assign(self.a_quantizer.zero_point, torch.gather(cz, dim=-1, index=idx).squeeze(-1))
 
     # ------------------------------------------------------------------ the four evaluations
     def _search_best_w_scale_self(self, weight_scale_candidates, weight_zero_point_candidates, topk=1):
@@ -374,8 +375,8 @@ class AsymmetricallyChannelWiseBatchingQuantLinear(AsymmetricallyBatchingQuantLi
 
 
 class PostGeluTwinUniformBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
-    """reference: quant_layers/linear.py:624-721 (PTQ4ViT twin-uniform baseline, post_gelu_quantizer='ptq4vit').
-    Constructor, state_dict and fake-quant forward are provided; its search is not on the AdaLog hot path."""
+    """reference: quant_layers/linear.py:624-721 (PTQ4ViT twin-uniform baseline, post_gelu_quantizer='ptq4vit'): a
+    positive-range scale searched over 29 power-of-two multiples of the fixed negative-range scale."""
 
     def __init__(self, in_features: int, out_features: int, bias: bool = True, mode="raw", w_bit=8, a_bit=8,
                  calib_batch_size=None, search_round=1, eq_n=100, n_V=1, fpcs=False, steps=4):
@@ -385,9 +386,49 @@ class PostGeluTwinUniformBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         self.a_quantizer = TwinUniformQuantizer(n_bits=a_bit, symmetric=False, channel_wise=False)
         self.a_quantizer.scale = nn.Parameter(torch.zeros((2, 1)))
 
+    def _initialize_activation_scale(self):
+        """reference linear.py:647-662: positive scale from the largest |x| (max over the 32-sample batches = global
+        max; all-reduced under data parallelism), negative scale = |min GELU| / n_levels"""
+        nl = self.a_quantizer.n_levels
+        dev = self.weight.device
+        amax = adist.all_reduce_max(self._ctx.x2d.abs().max().view(1))
+        pos = (amax / (nl - 0.5)).view(1)
+        neg = torch.tensor(GELU_MIN / nl, device=dev).view(1)
+        assign(self.a_quantizer.scale, torch.stack([pos, neg]))
+        self.a_quantizer.inited = True
+
+    def _search_best_a_scale(self, input_scale_candidates):
+        """reference linear.py:664-696: only the first shape[-1] - 1 candidates are scored (:665-666) and the winner is
+        taken with argmax (first maximum), not topk"""
+        n = input_scale_candidates.shape[-1] - 1
+        sims = sweep.linear_err_a_twin(self._ctx, self._weight3(), self.bias, self.w_quantizer,
+                                       self.a_quantizer.scale[1].detach(), input_scale_candidates[:, :n].contiguous(),
+                                       self.a_quantizer.n_levels)
+        best = sims.argmax(dim=0, keepdim=True).reshape(1, -1)
+        new_pos = torch.gather(input_scale_candidates, dim=-1, index=best).squeeze(-1)
+        assign(self.a_quantizer.scale, torch.stack([new_pos, self.a_quantizer.scale[1].detach().clone()]))
+        return best.squeeze(0)
+
     def hyperparameter_searching(self):
-        raise NotImplementedError("post_gelu_quantizer='ptq4vit' (twin-uniform baseline search, reference "
-                                  "linear.py:697-721) is outside the AdaLog FPCS hot path; use 'adalog'")
+        """reference linear.py:698-721"""
+        cls = AsymmetricallyBatchingQuantLinear
+        self._initialize_calib_parameters()
+        self._initialize_activation_scale()
+        if self.fpcs:
+            self.weight_fpcs(steps=self.steps, search_strategy=cls._search_best_w_scale_self)
+        else:
+            self._search_best_w_scale_self(*self.calculate_percentile_weight_candidates())
+        # in PTQ4ViT, delta_r2 = delta_r1 * 2^m
+        cands = (torch.tensor([(2 ** i) for i in range(-5, 25)]).to(self.weight.device).view(1, -1)
+                 * self.a_quantizer.scale[1].detach().unsqueeze(-1))
+        for _ in range(self.search_round):
+            self._search_best_a_scale(cands)
+            if self.fpcs:
+                self.weight_fpcs(steps=self.steps, search_strategy=cls._search_best_w_scale)
+            else:
+                self._search_best_w_scale(*self.calculate_percentile_weight_candidates())
+        self._finish()
+        return None
 
 
 class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
@@ -401,7 +442,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         del self.a_quantizer
         self.a_quantizer = ShiftAdaLogQuantizer(n_bits=a_bit, symmetric=False, channel_wise=False)
         self.a_quantizer.scale = nn.Parameter(torch.zeros((1)))
-        self.a_quantizer.shift.data.copy_(torch.tensor(GELU_MIN))
+        assign(self.a_quantizer.shift, torch.tensor(GELU_MIN))
         # search LUT (reference linear.py:750-752), kept for API parity; the kernels use its integer numerators
         self.table = torch.tensor([2 ** (-j / self.a_quantizer.r) for j in range(120)])
         self.table_scale = 1. / (4 * self.a_quantizer.n_levels - 2)
@@ -410,7 +451,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         if tmp_cls is not None:
             self.tmp_quantizer = tmp_cls(n_bits=a_bit, symmetric=False, channel_wise=False)
             self.tmp_quantizer.scale = nn.Parameter(torch.zeros((1)))
-            self.tmp_quantizer.shift.data.copy_(torch.tensor(GELU_MIN))
+            assign(self.tmp_quantizer.shift, torch.tensor(GELU_MIN))
 
     @staticmethod
     def positive_percentile(tensor, q, dim=0):
@@ -448,7 +489,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
                                     else self.positive_percentile(x, q))
         cand = cache[('pos', l, r)] + self.a_quantizer.shift.item()
         cand = cand.unsqueeze(0)
-        ramp = torch.tensor([i / (self.eq_n - 1) for i in range(self.eq_n)]).to(x.device).view(1, -1)
+        ramp = torch.tensor([i / (self.eq_n - 1) for i in range(self.eq_n)]).to(cand.device).view(1, -1)
         return cand, cand[:, 0:1] + (cand[:, 1:] - cand[:, 0:1]) * ramp
 
     def _log_scored(self, cs, cq):
@@ -468,7 +509,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         sims = self._log_scored(input_scale_candidates, self.a_quantizer.q.view(1, 1).expand(1, P))
         _, best = torch.topk(sims, k=topk, dim=-1)
         if topk == 1:
-            self.a_quantizer.scale.data.copy_(torch.gather(input_scale_candidates, dim=-1, index=best).squeeze(-1))
+            assign(self.a_quantizer.scale, torch.gather(input_scale_candidates, dim=-1, index=best).squeeze(-1))
             self.a_quantizer.update_table()
         return best
 
@@ -479,7 +520,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         sims = self._log_scored(None, q_candidates[:, :self.eq_n])
         _, best = torch.topk(sims, k=topk, dim=-1)
         if topk == 1:
-            self.a_quantizer.q.data.copy_(torch.gather(q_candidates, dim=-1, index=best).view(*self.a_quantizer.q.shape))
+            assign(self.a_quantizer.q, torch.gather(q_candidates, dim=-1, index=best).view(*self.a_quantizer.q.shape))
             self.a_quantizer.update_table()
         return best
 
@@ -488,8 +529,8 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         sims = self._log_scored(input_scale_candidates, q_candidates)
         _, best = torch.topk(sims, k=topk, dim=-1)
         if topk == 1:
-            self.a_quantizer.scale.data.copy_(torch.gather(input_scale_candidates, dim=-1, index=best).squeeze(-1))
-            self.a_quantizer.q.data.copy_(torch.gather(q_candidates, dim=-1, index=best).view(*self.a_quantizer.q.shape))
+            assign(self.a_quantizer.scale, torch.gather(input_scale_candidates, dim=-1, index=best).squeeze(-1))
+            assign(self.a_quantizer.q, torch.gather(q_candidates, dim=-1, index=best).view(*self.a_quantizer.q.shape))
             self.a_quantizer.update_table()
         return best
 
@@ -516,7 +557,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
             w_cs, w_cz = self.calculate_percentile_weight_candidates()
             self._search_best_w_scale_self(w_cs, w_cz)
         ud, a_cs = self.calculate_percentile_activation_candidates()
-        self.a_quantizer.scale.data.copy_(a_cs[:, -2])
+        assign(self.a_quantizer.scale, a_cs[:, -2])
         self.a_quantizer.inited = True
         for _ in range(self.search_round):
             if self.fpcs:
@@ -528,7 +569,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
                 w_cs, w_cz = self.calculate_percentile_weight_candidates()
                 self._search_best_w_scale(w_cs, w_cz)
         if hasattr(self, 'tmp_quantizer'):
-            self.tmp_quantizer.scale.data.copy_(self.a_quantizer.scale.data)
+            assign(self.tmp_quantizer.scale, self.a_quantizer.scale.data)
             self.tmp_quantizer.inited = True
             self.a_quantizer = self.tmp_quantizer
             del self.tmp_quantizer
@@ -540,6 +581,5 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
             return
         x_ = torch.full((1, self.in_features), -self.a_quantizer.shift.item(), device=self.weight.device)
         w_sim, bias_sim = self.quant_weight_bias()
-        self.bias.data.copy_(bias_sim + (x_ @ w_sim.transpose(0, 1)).squeeze())
-        self.a_quantizer.bias_reparamed.data.copy_(torch.tensor(True))
-        self.a_quantizer.bias_reparamed._adalog_flag = None      # (.data writes do not bump the version counter)
+        assign(self.bias, bias_sim + (x_ @ w_sim.transpose(0, 1)).squeeze())
+        assign(self.a_quantizer.bias_reparamed, torch.tensor(True))

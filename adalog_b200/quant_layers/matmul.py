@@ -12,6 +12,7 @@ from .. import sweep
 from ..quantizers.uniform import UniformQuantizer
 from ..quantizers.logarithm import Log2Quantizer, LogSqrt2Quantizer, AdaLogQuantizer
 from ..utils import dist as adist
+from ..quantizers._ste import assign
 from . import _fpcs
 
 __all__ = ['MinMaxQuantMatMul', 'PTQSLQuantMatMul', 'PTQSLBatchingQuantMatMul', 'AsymmetricallyBatchingQuantMatMul',
@@ -86,6 +87,7 @@ class PTQSLBatchingQuantMatMul(PTQSLQuantMatMul):
         sweep.require_cuda(dev)
         self.calib_size = self.raw_input[0].shape[0]
         self.parallel_eq_n = self.eq_n
+        self.__dict__.pop('_pct_cache', None)
         self._ctx = sweep.MatMulCtx(self.raw_input[0].to(dev), self.raw_input[1].to(dev), self.raw_out.to(dev))
 
 
@@ -114,8 +116,8 @@ class AsymmetricallyBatchingQuantMatMul(PTQSLBatchingQuantMatMul):
         _, best = torch.topk(sims, k=topk, dim=0)
         best = best.view(topk, 1, -1, 1, 1)
         if topk == 1:
-            quantizer.scale.data.copy_(torch.gather(cs, dim=0, index=best).view(quantizer.scale.shape))
-            quantizer.zero_point.data.copy_(torch.gather(cz, dim=0, index=best).view(quantizer.zero_point.shape))
+            assign(quantizer.scale, torch.gather(cs, dim=0, index=best).view(quantizer.scale.shape))
+            assign(quantizer.zero_point, torch.gather(cz, dim=0, index=best).view(quantizer.zero_point.shape))
         return best
 
     def _search_best_A_scale(self, A_scale_candidates, A_zero_point_candidates, topk=1):
@@ -142,7 +144,8 @@ class AsymmetricallyBatchingQuantMatMul(PTQSLBatchingQuantMatMul):
         key = (x.data_ptr(), tuple(x.shape), x._version, bool(self.head_channel_wise), l, r)
         cache = self.__dict__.setdefault('_pct_cache', {})
         if key not in cache:
-            cache.clear()
+            if len(cache) >= 2:                    # one entry per operand (A and B alternate inside a search round)
+                cache.clear()
             if self.head_channel_wise:             # x: this rank's samples; chunked_quantile selects across ranks
                 x_ = x.transpose(0, 1).contiguous()
                 x_ = x_.view(x_.shape[0], 1, -1)
@@ -163,14 +166,15 @@ class AsymmetricallyBatchingQuantMatMul(PTQSLBatchingQuantMatMul):
         return self.raw_input[i].to(self._device())
 
     def _seed(self, quantizer, cs, cz):
-        quantizer.scale.data.copy_(cs[-2])
-        quantizer.zero_point.data.copy_(cz[-2])
+        assign(quantizer.scale, cs[-2])
+        assign(quantizer.zero_point, cz[-2])
         quantizer.inited = True
 
     def _finish(self):
         self.calibrated = True
         del self.raw_input, self.raw_out
         self._ctx = None
+        self.__dict__.pop('_pct_cache', None)      # the sorted operands belong to this calibration only
 
     def hyperparameter_searching(self):
         """reference matmul.py:264-283"""
@@ -224,7 +228,7 @@ class PostSoftmaxAsymmetricallyBatchingQuantMatMul(AsymmetricallyBatchingQuantMa
         _, best = torch.topk(sims, k=topk, dim=0)
         best = best.view(topk, 1, 1, 1, 1)
         if topk == 1:
-            self.A_quantizer.q.data.copy_(torch.gather(q_candidates, dim=0, index=best).view(*self.A_quantizer.q.shape))
+            assign(self.A_quantizer.q, torch.gather(q_candidates, dim=0, index=best).view(*self.A_quantizer.q.shape))
             self.A_quantizer.update_table()
         return best
 

@@ -14,6 +14,30 @@ def ceil_ste(x: torch.Tensor):
     return (x.ceil() - x).detach() + x
 
 
+def assign(p, value):
+    """p <- value in place THROUGH the tensor itself (not `.data`), so that p._version is bumped: the caches keyed on
+    (data_ptr, _version) -- round_ste(zero_point) in ops.py, the tensor-core weight operand in sweep.py, flag() below --
+    see every write this package makes to quantizer state, weights and biases.  (External code that writes through
+    `.data`, as the reference's BRECQ does, must call `invalidate_caches(module)`.)"""
+    with torch.no_grad():
+        p.copy_(value.to(p.device) if isinstance(value, torch.Tensor) else value)
+    return p
+
+
+def invalidate_caches(module):
+    """Forget every derived tensor cached on `module` and its quantizers (after an external write through `.data`)."""
+    for m in module.modules():
+        m.__dict__.pop('_tc_cache', None)
+        m.__dict__.pop('_pct_cache', None)
+        for t in list(m.parameters(recurse=False)) + list(m.buffers(recurse=False)):
+            for attr in ('_adalog_zr', '_adalog_flag'):
+                if hasattr(t, attr):
+                    try:
+                        delattr(t, attr)
+                    except AttributeError:
+                        pass
+
+
 def flag(t):
     """bool(t) for a 0-d flag buffer (e.g. `bias_reparamed`) without a device synchronisation on every inference
     forward: under no_grad the value is read once and remembered on the tensor until it is modified in place or moved

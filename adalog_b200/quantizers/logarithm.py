@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._ste import flag, round_ste
+from ._ste import assign, flag, round_ste
 
 __all__ = ['Log2Quantizer', 'LogSqrt2Quantizer', 'AdaLogQuantizer', 'ShiftLog2Quantizer', 'ShiftLogSqrt2Quantizer',
            'ShiftAdaLogQuantizer']
@@ -105,8 +105,8 @@ class AdaLogQuantizer(Log2Quantizer):
         n = self.n_levels
         t1 = [math.floor(i * q / self.r) for i in range(2 * n)]
         t2 = [round((2 ** (-((q * i) % self.r) / self.r)) * (4 * n - 2)) / (4 * n - 2) for i in range(2 * n)]
-        self.table1.data.copy_(torch.tensor(t1, dtype=torch.float32))
-        self.table2.data.copy_(torch.tensor(t2, dtype=torch.float32))
+        assign(self.table1, torch.tensor(t1, dtype=torch.float32))
+        assign(self.table2, torch.tensor(t2, dtype=torch.float32))
 
     def _ste_dequant(self, scaled_x):
         x_quant = round_ste(-scaled_x.log2() * self.r / self.q)

@@ -134,7 +134,7 @@ def run_cand_gemm(gen_cand, U, ka, UG, Bm, brpg, N, y, ldy, rs, rb=None, rs_div=
     max_units = max(1, (WS_BYTES // 2) // unit_elems)
     step = min(U, max_units) if single else min(U, max(1, max_units // UG) * UG)
     n_chunks = (U + step - 1) // step
-    BN = ops.pick_bn(N)
+    BN = ops.pick_bn(N, 32 if rb is not None else 16)
     NT = (N + BN - 1) // BN
     overlap = OVERLAP and n_chunks > 1 and dev.type == 'cuda'
     ws_all = _workspace(dev, (2 if overlap else 1) * step * unit_elems)
@@ -203,6 +203,7 @@ class LinearCtx:
         self.x2d = _f32(raw_input).reshape(-1, raw_input.shape[-1])
         self.y2d = _f32(raw_out).reshape(-1, out_features)
         self.n_samples = raw_input.shape[0]
+        adist.check_equal_shards(self.n_samples, 'linear raw_input')
         self.tok_per_sample = self.x2d.shape[0] // self.n_samples
         self._yT = None
 
@@ -247,21 +248,36 @@ def _i8_ok(*n_levels):
     return USE_I8 and all(nl <= 64 for nl in n_levels)
 
 
+def _is_adalog(q):
+    return getattr(q, 'is_log', False) and hasattr(q, 'table2')
+
+
+def _generic_fixed_operand(q, x2d):
+    """A fake-quantised tensor with no (integer x one scale) form -- TwinUniform (two scales), Log2 / LogSqrt2 with
+    their FP32 sqrt(2) factor and shift -- enters the tensor cores exactly as THREE bf16 pieces of its FP32 value
+    (gen_split3, the patch-embedding trick): fixed operand [x_h | x_m | x_l], candidate operand replicated 3x along K."""
+    with torch.no_grad():
+        return ops.gen_split3(q(x2d))
+
+
 def _fixed_act_operand(ctx, aq, i8=False):
     """quant_input(x) as an exact bf16 / int8 operand + the epilogue factors it implies.
 
-    returns (Bm [tokens, ka], a_scale (python float tensor [1] FP64), shift or None)
+    returns (Bm [tokens, krep * ka], a_scale FP64 [1], shift or None, krep)
     uniform:       x_hat = a_scale * I
     shift-adalog:  x_hat = a_scale/(4n-2) * (m 2^-e) - shift        (logarithm.py:127-135, not bias-reparamed)
+    anything else: x_hat itself as three bf16 pieces (krep = 3)
     """
-    if getattr(aq, 'is_log', False):
+    if _is_adalog(aq):
         nl = aq.n_levels
         m2 = torch.round(_f32(aq.table2) * (4 * nl - 2))
         Bm = ops.gen_log_fixed(ctx.x2d, aq.scale, aq.q, aq.shift, aq.table1, m2, nl)
-        return Bm, _f32(aq.scale).double().reshape(1) / (4 * nl - 2), _f32(aq.shift).double().reshape(1)
+        return Bm, _f32(aq.scale).double().reshape(1) / (4 * nl - 2), _f32(aq.shift).double().reshape(1), 1
+    if getattr(aq, 'is_log', False) or type(aq).__name__ != 'UniformQuantizer':
+        return _generic_fixed_operand(aq, ctx.x2d), torch.ones(1, dtype=torch.float64, device=ctx.x2d.device), None, 3
     s, z = uniform_operand_params(aq)
     Bm, _ = ops.gen_uniform_fixed(ctx.x2d, s, z, 1 << 62, 1, aq.n_levels, i8=i8)
-    return Bm, s.double(), None
+    return Bm, s.double(), None, 1
 
 
 def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
@@ -271,9 +287,9 @@ def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
     P = cs.shape[0]
     dev = weight3.device
     c2, z2 = _cand2d(cs, cz)                         # [P, out]
-    i8 = not getattr(aq, 'is_log', False) and _i8_ok(aq.n_levels, n_levels_w)
-    Bm, a_scale, shift = _fixed_act_operand(ctx, aq, i8)
-    ka = ops.kpad(in_f, i8)
+    i8 = type(aq).__name__ == 'UniformQuantizer' and _i8_ok(aq.n_levels, n_levels_w)
+    Bm, a_scale, shift, krep = _fixed_act_operand(ctx, aq, i8)
+    ka = krep * ops.kpad(in_f, i8)
     W2d = _f32(weight3).reshape(out_f, in_f)
     c2p = _pad128(c2.t().contiguous())               # [out, 128] candidate scales per row
     rs = (c2p.double() * a_scale).float().contiguous()
@@ -282,7 +298,7 @@ def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
     rowsum = torch.empty(out_f, ops.P_TILE, dtype=torch.float32, device=dev) if shift is not None else None
 
     def gen(u0, nu, out):
-        ops.gen_uniform_cand(W2d, u0, nu, c2, z2, P, out_f, 1, 1, out_f, n_levels_w, out, 1,
+        ops.gen_uniform_cand(W2d, u0, nu, c2, z2, P, out_f, 1, 1, out_f, n_levels_w, out, krep,
                              rowsum[u0:] if rowsum is not None else None, i8=i8)
         if shift is not None:
             # sum_k (v s - shift) w = s sum_k v w - shift sum_k w  (linear.py:879): fold the second term into the
@@ -356,8 +372,9 @@ def linear_quant_forward(x2d, weight3, bias, wq, aq, cache=None):
     return ops.gemm_dequant(A, M, Bm, ka, out_f, rs, s_w.contiguous(), b.contiguous(), upc, S, i8, sf)
 
 
-def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
-    """linear.py:394-423 -> similarities [1, P]."""
+def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a, y2d=None):
+    """linear.py:394-423 -> similarities [1, P].  y2d: score against this target instead of raw_out (the twin-uniform
+    search folds its fixed negative branch into it)."""
     n_V, rows, in_f = weight3.shape
     out_f = n_V * rows
     P = cs.shape[-1]
@@ -373,10 +390,28 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
     rs = _pad128(c1).contiguous()
     cb = _f32(bias) if bias is not None else torch.zeros(out_f, device=dev)
     ntok = ctx.x2d.shape[0]
-    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
+    y = ctx.y2d if y2d is None else y2d
+    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, y, out_f, rs, None, 1 << 62, 1, s_w, cb,
                         k_true=in_f, i8=i8)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
     return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
+
+
+def linear_err_a_twin(ctx, weight3, bias, wq, s_neg, cands, n_levels):
+    """linear.py:664-690 (PTQ4ViT twin-uniform baseline): x_hat_p = clamp(rint(x/s_p), 0, n-1) s_p + x_neg with the
+    negative branch x_neg = clamp(rint(x/s_neg), -n, 0) s_neg fixed.  The candidate branch is a uniform quantizer with
+    zero point 0 and n levels (the device sweep of linear_err_a with n_levels/2); the fixed branch's contribution
+    F.linear(x_neg, W_hat) is computed once and folded into the target.  -> similarities [P]."""
+    n_V, rows, in_f = weight3.shape
+    out_f = n_V * rows
+    with torch.no_grad():
+        w_hat = wq(weight3).reshape(out_f, in_f)
+        x_neg = (ctx.x2d / s_neg.reshape(1)).round_().clamp_(-n_levels, 0) * s_neg.reshape(1)
+        target = ctx.y2d - torch.nn.functional.linear(x_neg, w_hat)
+    if n_levels < 2 or n_levels % 2:
+        raise NotImplementedError('twin-uniform search needs n_bits >= 2')
+    sims = linear_err_a(ctx, weight3, bias, wq, cands, torch.zeros_like(cands), n_levels // 2, y2d=target.contiguous())
+    return sims.reshape(-1)
 
 
 def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
@@ -417,6 +452,7 @@ class MatMulCtx:
         self.raw_input, self.raw_out = [A, B], raw_out
         A, B, raw_out = _f32(A), _f32(B), _f32(raw_out)
         self.Bn, self.H, self.S1, self.Kd = A.shape
+        adist.check_equal_shards(self.Bn, 'matmul raw_input')
         self.S2 = B.shape[-1]
         self.A2d = A.reshape(-1, self.Kd)                                   # rows (b,h,s1)
         self.Bt2d = B.transpose(-2, -1).contiguous().reshape(-1, self.Kd)   # rows (b,h,s2)
@@ -510,19 +546,19 @@ def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, head_channel_wise):
 
 
 def _fixed_A_operand(ctx, Aq, i8=False):
-    """quant_input_A(A) as a bf16 (or int8) operand, rows (b,h,s1); returns (Bm, per-head scale FP64 [H])."""
+    """quant_input_A(A) as a bf16 (or int8) operand, rows (b,h,s1); returns (Bm, per-head scale FP64 [H], krep)."""
     H = ctx.H
-    if getattr(Aq, 'is_log', False):
-        if not hasattr(Aq, 'table2'):
-            raise NotImplementedError("post_softmax_quantizer 'log2' / 'logsqrt2' (fixed-base baselines, reference "
-                                      "matmul.py:307-310) have no device sweep; use 'adalog'")
+    if _is_adalog(Aq):
         nl = Aq.n_levels
         m2 = torch.round(_f32(Aq.table2) * (4 * nl - 2))
         Bm = ops.gen_log_fixed(ctx.A2d, Aq.scale, Aq.q, None, Aq.table1, m2, nl)
-        return Bm, (_f32(Aq.scale).double().reshape(1) / (4 * nl - 2)).expand(H)
+        return Bm, (_f32(Aq.scale).double().reshape(1) / (4 * nl - 2)).expand(H), 1
+    if getattr(Aq, 'is_log', False):
+        # post_softmax_quantizer 'log2' / 'logsqrt2' (matmul.py:307-310): per-tensor scale, values 2^-k [x sqrt(2)]
+        return _generic_fixed_operand(Aq, ctx.A2d), torch.ones(H, dtype=torch.float64, device=ctx.A2d.device), 3
     sA, zA = _head_params(Aq, H)
     Bm, _ = ops.gen_uniform_fixed(ctx.A2d, sA, zA, ctx.S1, H, Aq.n_levels, i8=i8)
-    return Bm, sA.double()
+    return Bm, sA.double(), 1
 
 
 def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, head_channel_wise):
@@ -532,12 +568,12 @@ def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, head_channel_wise):
     c2, z2 = _cand2d(cs, cz)
     gs = 1 if c2.shape[1] == H else 0
     i8 = False
-    fused = _use_fused(ctx.Kd, ctx.S1, i8, False, n_levels_B)
-    Bm, sA = _fixed_A_operand(ctx, Aq, i8)
-    ka = ops.kpad(ctx.Kd)
+    Bm, sA, krep = _fixed_A_operand(ctx, Aq, i8)
+    fused = krep == 1 and _use_fused(ctx.Kd, ctx.S1, i8, False, n_levels_B)
+    ka = krep * ops.kpad(ctx.Kd)
 
     def gen(u0, nu, out):
-        ops.gen_uniform_cand(ctx.Bt2d, u0, nu, c2, z2, P, c2.shape[1], gs, ctx.S2, H, n_levels_B, out)
+        ops.gen_uniform_cand(ctx.Bt2d, u0, nu, c2, z2, P, c2.shape[1], gs, ctx.S2, H, n_levels_B, out, krep)
 
     cfull = c2 if gs else c2.expand(P, H)
     rs = (_pad128(cfull.t().contiguous()).double() * sA.reshape(H, 1)).float().contiguous()
@@ -588,6 +624,7 @@ class ConvCtx:
         oh, ow = Hh // kh, Ww // kw
         patches = x.reshape(Bn, ic, oh, kh, ow, kw).permute(0, 2, 4, 1, 3, 5).reshape(Bn * oh * ow, ic * kh * kw)
         self.n_samples = Bn
+        adist.check_equal_shards(Bn, 'conv raw_input')
         self.pos_per_sample = oh * ow
         self.x3 = ops.gen_split3(patches.contiguous())                 # [tokens, 3*ka]
         oc = y.shape[1]

@@ -21,11 +21,33 @@ def rank():
     return dist.get_rank() if active() else 0
 
 
+def check_equal_shards(n_local, what='calibration tensor'):
+    """Every rank must hold the same number of samples: the order statistics (n_glob = n_local * ranks), the 2^24 chunk
+    rule and all_gather_cat assume it, and the GPU-count-invariant partial sums need shards of whole 32-token slabs."""
+    if not active():
+        return
+    t = torch.tensor([n_local, -n_local], dtype=torch.int64)
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    t = t.to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if int(t[0]) != -int(t[1]):
+        raise ValueError(f'{what}: ranks hold different numbers of samples ({-int(t[1])}..{int(t[0])}); '
+                         f'shard the calibration set evenly (calib_size % world_size == 0)')
+
+
 def all_reduce_sum(t):
     """In-place SUM all-reduce of an error-sum tensor (identity when not distributed)."""
     if active():
         t = t.contiguous()
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def all_reduce_max(t):
+    """In-place MAX all-reduce (identity when not distributed)."""
+    if active():
+        t = t.contiguous()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t
 
 

@@ -315,6 +315,8 @@ MODEL_ZOO = {
     # one-block DeiT-Tiny: the ncu launch-list target (profiles/)
     'deit_tiny_depth1_patch16_224': lambda: VisionTransformer(embed_dim=192, depth=1, num_heads=3),
     'deit_small_depth2_patch16_224': lambda: VisionTransformer(embed_dim=384, depth=2, num_heads=6),
+    # patch embedding + block 0 + head of DeiT-Small: the free-running parity slice of BASELINE config 2
+    'deit_small_depth1_patch16_224': lambda: VisionTransformer(embed_dim=384, depth=1, num_heads=6),
     # tiny configurations for tests
     'vit_test_patch8_32': lambda: VisionTransformer(img_size=32, patch_size=8, num_classes=10, embed_dim=32, depth=2,
                                                     num_heads=2),

@@ -30,8 +30,9 @@ SHIFT_GELU = 0.16997124254703522  # linear.py:749 (|min GELU|)
 R_BASE = 37.0                     # logarithm.py:71
 
 # None: contractions run in FP32 exactly like the reference.  torch.float64: the quantisation decisions stay FP32
-# (bit-identical operands) but F.linear / @ / F.conv2d and the error reduction run in FP64 -- the "infinitely
-# precise reference" used by the tests to show which side of a 1e-5 disagreement is the FP32 rounding noise.
+# (bit-identical operands) but F.linear / @ / F.conv2d and the error reduction (also of the self-error sweeps) run in
+# FP64 -- the "infinitely precise reference" used by the tests to show which side of a 1e-5 disagreement is the FP32
+# rounding noise.
 GEMM_DTYPE = None
 
 
@@ -51,6 +52,13 @@ class Trace:
     def topk(self, sims, k, dim, tag=''):
         _, idx = torch.topk(sims, k=k, dim=dim)
         self.evals.append(dict(tag=tag, sims=sims.detach().clone(), k=k, dim=dim, idx=idx.clone()))
+        return idx
+
+    def argmax(self, sims, tag=''):
+        """the one selection the reference makes with Tensor.argmax instead of topk (linear.py:691); its tie order
+        differs from topk's, so it is recorded (and replayed) as what it is"""
+        idx = sims.argmax(dim=0, keepdim=True)
+        self.evals.append(dict(tag=tag, sims=sims.detach().clone(), k=1, dim=0, idx=idx.clone(), argmax=True))
         return idx
 
 
@@ -200,6 +208,40 @@ class LQ:
             return adalog_fakequant(x, self.scale, self.q, self.n_levels, self.table1, self.table2)
         return shift_fakequant(adalog_fakequant, x, self.shift, self.bias_reparamed, self.scale, self.q,
                                self.n_levels, self.table1, self.table2)
+
+
+@dataclass
+class FixedLogQ:
+    """(Shift)Log2Quantizer / (Shift)LogSqrt2Quantizer state (logarithm.py:8-65, 105-124)."""
+    kind: str
+    n_bits: int
+    scale: Optional[torch.Tensor] = None
+    shift: Optional[torch.Tensor] = None
+    bias_reparamed: bool = False
+
+    @property
+    def n_levels(self):
+        return 2 ** (self.n_bits - 1)
+
+    def __call__(self, x):
+        fn = log2_fakequant if self.kind == 'log2' else logsqrt2_fakequant
+        if self.shift is None:
+            return fn(x, self.scale, self.n_levels)
+        return shift_fakequant(fn, x, self.shift, self.bias_reparamed, self.scale, self.n_levels)
+
+
+@dataclass
+class TQ:
+    """TwinUniformQuantizer state (uniform.py:53-68): scale [2, 1]."""
+    n_bits: int
+    scale: Optional[torch.Tensor] = None
+
+    @property
+    def n_levels(self):
+        return 2 ** (self.n_bits - 1)
+
+    def __call__(self, x):
+        return twin_uniform_fakequant(x, self.scale, self.n_levels)
 
 
 def _wview(weight, n_V):
@@ -385,6 +427,8 @@ class LinearSearch:
         self.a_channel_wise = a_channel_wise
         if a_kind == 'uniform':
             self.aq = UQ(a_bit)
+        elif a_kind == 'twin':
+            self.aq = TQ(a_bit, scale=torch.zeros(2, 1).to(weight.device))
         else:
             self.aq = LQ(a_bit, shift=torch.tensor([SHIFT_GELU]).to(weight.device))
             self.aq.q = self.aq.q.to(weight.device)
@@ -413,7 +457,7 @@ class LinearSearch:
             s, z = cs[p0:p1], cz[p0:p1]
             wq = ((raw / s).round_() + z).clamp(0, L)
             wd = (wq - z) * s
-            sims.append(torch.mean(_sim(raw, wd), dim=-1, keepdim=False))
+            sims.append(torch.mean(_sim(*_up(raw, wd)), dim=-1, keepdim=False))
         return torch.cat(sims, dim=0)
 
     def eval_w_self(self, cs, cz, topk=1):
@@ -436,7 +480,7 @@ class LinearSearch:
                 s, z = cs[:, p0:p1], cz[:, p0:p1]
                 xq = ((x.unsqueeze(-1) / s).round_() + z).clamp_(0, L)
                 xd = (xq - z) * s
-                sim = _sim(raw_x, xd)
+                sim = _sim(*_up(raw_x, xd))
                 if sim.dim() > 3:
                     sim = torch.mean(sim, dim=list(range(1, sim.dim() - 2)))
                 if not self.a_channel_wise:
@@ -619,16 +663,101 @@ class LinearSearch:
         qc = torch.gather(q_all, dim=-1, index=q_idx).repeat_interleave(scale_num, dim=-1)
         _fpcs_tail(cs, qc, delta, self.eval_scale_logbase, -1, int(self.eq_n / width), width, self.steps, None, dev)
 
-    def search_postgelu(self):
-        """linear.py:969-997 (adalog quantizer)."""
+    def eval_a_log_scale(self, cs, topk=1):
+        """linear.py:816-854: scale-only search at the current base (the fpcs=False path)."""
+        sims = self._a_out_sims(lambda x4, p0, p1: self._log_xsim(x4, cs[:, p0:p1], self.aq.q))
+        idx = self.trace.topk(sims, topk, -1, 'log_scale')
+        if topk == 1:
+            self.aq.scale = torch.gather(cs, -1, idx).squeeze(-1)
+            self.aq.update_table()
+        return idx
+
+    def search_postgelu(self, tmp_kind=None):
+        """linear.py:969-997.  tmp_kind 'log2' / 'logsqrt2': the fixed-base quantizer swapped in after the AdaLog
+        search (:990-994)."""
         self.init_calib()
-        self.weight_fpcs(self.eval_w_self)
+        nl = self.wq.n_levels
+        if self.fpcs_on:
+            self.weight_fpcs(self.eval_w_self)
+        else:
+            self.eval_w_self(*weight_candidates(self.weight, self.n_V, nl, self.eq_n))
         ud, sc = postgelu_candidates(self.raw_input, self.aq.shift.item(), self.eq_n)
         self.aq.scale = sc[:, -2].clone()
         self.aq.update_table()
         for _ in range(self.search_round):
-            self.postgelu_activation_fpcs(ud)
-            self.weight_fpcs(self.eval_w)
+            if self.fpcs_on:
+                self.postgelu_activation_fpcs(ud)
+                self.weight_fpcs(self.eval_w)
+            else:
+                self.eval_log_base()
+                self.eval_a_log_scale(sc)
+                self.eval_w(*weight_candidates(self.weight, self.n_V, nl, self.eq_n))
+        if tmp_kind is not None:
+            self.aq = FixedLogQ(tmp_kind, self.aq.n_bits, scale=self.aq.scale.clone(), shift=self.aq.shift)
+
+    # -- PostGeluTwinUniformBatchingQuantLinear, linear.py:624-721 (PTQ4ViT twin-uniform baseline)
+    def twin_init_scale(self):
+        """linear.py:647-662."""
+        nl = self.aq.n_levels
+        per_batch = []
+        for b0, b1 in self._batches():
+            x = self.raw_input[b0:b1]
+            per_batch.append((x.abs().max() / (nl - 0.5)).view(1, 1).expand(1, self.aq.scale.shape[-1]))
+        pos = torch.cat(per_batch, dim=0).amax(dim=0, keepdim=False).view(-1)
+        neg = torch.tensor(SHIFT_GELU / nl, device=self.aq.scale.device).view(1).repeat(self.aq.scale.shape[-1])
+        self.aq.scale = torch.stack([pos, neg]).clone()
+
+    def sims_a_twin(self, cands):
+        """linear.py:664-690: only the first cands.shape[-1] - 1 candidates are scored (:665-666)."""
+        nl = self.aq.n_levels
+        n = cands.shape[-1] - 1
+        s_neg = self.aq.scale[1].unsqueeze(-1)
+        per_batch = []
+        for b0, b1 in self._batches():
+            x = self.raw_input[b0:b1]
+            ro = self.raw_out[b0:b1].unsqueeze(-2)
+            parts = []
+            for p0 in range(0, n, self.peq):
+                p1 = min(n, p0 + self.peq)
+                cur = cands[:, p0:p1]
+                w_sim = quant_weight(self.weight, self.wq, self.n_V)
+                x4 = x.unsqueeze(-1)
+                x_pos = (x4 / cur).round_().clamp_(0, nl - 1) * cur
+                x_neg = (x4 / s_neg).round_().clamp_(-nl, 0) * s_neg
+                xs = x_pos + x_neg
+                xs = xs.permute(*list(range(xs.dim() - 2)), -1, -2)
+                out = F.linear(*_up(xs, w_sim, self.bias))
+                sim = torch.mean(_sim(_up(ro)[0], out), dim=-1)
+                if sim.dim() > 2:
+                    sim = torch.mean(sim, dim=list(range(1, sim.dim() - 1)))
+                parts.append(torch.sum(sim, dim=0, keepdim=True))
+            per_batch.append(torch.cat(parts, dim=1))
+        return torch.cat(per_batch, dim=0).sum(dim=0, keepdim=False)
+
+    def eval_a_twin(self, cands):
+        """linear.py:664-696 (argmax, not topk)."""
+        sims = self.sims_a_twin(cands)
+        idx = self.trace.argmax(sims, 'a_twin').reshape(1, -1)
+        self.aq.scale = torch.stack([torch.gather(cands, -1, idx).squeeze(-1), self.aq.scale[1]])
+        return idx.squeeze(0)
+
+    def search_twin(self):
+        """linear.py:698-721."""
+        self.init_calib()
+        self.twin_init_scale()
+        nl = self.wq.n_levels
+        if self.fpcs_on:
+            self.weight_fpcs(self.eval_w_self)
+        else:
+            self.eval_w_self(*weight_candidates(self.weight, self.n_V, nl, self.eq_n))
+        cands = torch.tensor([(2 ** i) for i in range(-5, 25)]).to(self.weight.device).view(1, -1) \
+            * self.aq.scale[1].unsqueeze(-1)
+        for _ in range(self.search_round):
+            self.eval_a_twin(cands)
+            if self.fpcs_on:
+                self.weight_fpcs(self.eval_w)
+            else:
+                self.eval_w(*weight_candidates(self.weight, self.n_V, nl, self.eq_n))
 
     def reparam_bias(self):
         """linear.py:999-1006."""
@@ -645,7 +774,8 @@ class MatMulSearch:
     """matmul.py:109-283 (Q.K^T) and :286-378 (post-softmax P.V, AdaLog on A)."""
 
     def __init__(self, A, B, raw_out, A_bit, B_bit, num_heads, eq_n=128, calib_batch_size=32, search_round=3,
-                 steps=6, head_channel_wise=True, memory=8 * 2 ** 30, trace=None, post_softmax=False):
+                 steps=6, head_channel_wise=True, memory=8 * 2 ** 30, trace=None, post_softmax=False,
+                 quantizer='adalog'):
         self.A, self.B, self.raw_out = A, B, raw_out
         self.H, self.eq_n, self.bs = num_heads, eq_n, calib_batch_size
         self.search_round, self.steps, self.hcw = search_round, steps, head_channel_wise
@@ -653,7 +783,10 @@ class MatMulSearch:
         self.trace = trace or Trace()
         self.post_softmax = post_softmax
         self.Bq = UQ(B_bit)
-        if post_softmax:
+        self.adaptive = quantizer == 'adalog'
+        if post_softmax and not self.adaptive:      # matmul.py:307-310: fixed-base baselines, scale 1, nothing to search
+            self.Aq = FixedLogQ(quantizer, A_bit, scale=torch.ones(1, 1, 1, 1).to(A.device))
+        elif post_softmax:
             self.Aq = LQ(A_bit, scale=torch.ones(1, 1, 1, 1).to(A.device))
             self.Aq.q = self.Aq.q.to(A.device)
             self.Aq.update_table()
@@ -764,10 +897,13 @@ class MatMulSearch:
         self._init_from(self.Bq, self.B)
         for _ in range(self.search_round):
             if self.post_softmax:
-                self.eval_A_log_base()
+                if self.adaptive:
+                    self.eval_A_log_base()
             else:
                 self._fpcs(self.A, self.eval_A)
             self._fpcs(self.B, self.eval_B)
+            if self.post_softmax and not self.adaptive:
+                break                                   # matmul.py:374-375
 
 
 # ----------------------------------------------------------------------------------------------

@@ -21,9 +21,14 @@ OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 
 
 class TopkTap:
-    def __init__(self):
+    """records every torch.topk (and, with argmax=True, every Tensor.argmax: the twin-uniform search of linear.py:691
+    selects with argmax) as (similarities, k, dim, indices)"""
+
+    def __init__(self, argmax=False):
         self.evals = []
         self._orig = torch.topk
+        self._orig_argmax = torch.Tensor.argmax
+        self._argmax = argmax
 
     def __enter__(self):
         def tapped(inp, k, dim=-1, **kw):
@@ -31,10 +36,20 @@ class TopkTap:
             self.evals.append(dict(sims=inp.detach().clone(), k=k, dim=dim, idx=res[1].clone()))
             return res
         torch.topk = tapped
+        if self._argmax:
+            orig = self._orig_argmax
+
+            def tapped_argmax(t, *a, **kw):
+                res = orig(t, *a, **kw)
+                self.evals.append(dict(sims=t.detach().clone(), k=1, dim=kw.get('dim', a[0] if a else None),
+                                       idx=res.clone(), argmax=True))
+                return res
+            torch.Tensor.argmax = tapped_argmax
         return self
 
     def __exit__(self, *a):
         torch.topk = self._orig
+        torch.Tensor.argmax = self._orig_argmax
 
 
 def lnlike(*shape):
@@ -55,11 +70,11 @@ def sd(module):
 
 
 def run_linear(name, cls_name, in_f, out_f, x, w_bit, a_bit, n_V=1, bs=4, total_memory=None, bias=True, seed=0,
-               **extra):
+               fpcs=True, **extra):
     import quant_layers
     ref_shim.install(total_memory if total_memory is not None else 16 * 2 ** 30)
     cls = getattr(quant_layers, cls_name)
-    m = cls(in_f, out_f, bias=bias, w_bit=w_bit, a_bit=a_bit, calib_batch_size=bs, eq_n=128, fpcs=True, steps=6,
+    m = cls(in_f, out_f, bias=bias, w_bit=w_bit, a_bit=a_bit, calib_batch_size=bs, eq_n=128, fpcs=fpcs, steps=6,
             search_round=3, n_V=n_V, **extra)
     torch.manual_seed(seed + 100)
     torch.nn.init.trunc_normal_(m.weight, std=.02)
@@ -67,7 +82,7 @@ def run_linear(name, cls_name, in_f, out_f, x, w_bit, a_bit, n_V=1, bs=4, total_
     if bias:
         m.bias.data = torch.randn(out_f) * 0.02
     rec = dict(kind=cls_name, cfg=dict(in_f=in_f, out_f=out_f, w_bit=w_bit, a_bit=a_bit, n_V=n_V, bs=bs, bias=bias,
-                                      memory=ref_shim._Props.total_memory // 2),
+                                      memory=ref_shim._Props.total_memory // 2, fpcs=fpcs, **extra),
                weight=m.weight.detach().clone(), bias=m.bias.detach().clone() if bias else None, x=x.clone())
     ln = None
     if cls_name == 'AsymmetricallyChannelWiseBatchingQuantLinear':
@@ -76,7 +91,7 @@ def run_linear(name, cls_name, in_f, out_f, x, w_bit, a_bit, n_V=1, bs=4, total_
         ln.bias.data = 0.1 * torch.randn(in_f)
         m.prev_layer = ln
         rec['ln_weight'], rec['ln_bias'] = ln.weight.detach().clone(), ln.bias.detach().clone()
-    with torch.no_grad(), TopkTap() as tap:
+    with torch.no_grad(), TopkTap(argmax='Twin' in cls_name) as tap:
         m.raw_input = x
         m.raw_out = m(x)
         rec['raw_out'] = m.raw_out.clone()
@@ -101,16 +116,16 @@ def run_linear(name, cls_name, in_f, out_f, x, w_bit, a_bit, n_V=1, bs=4, total_
     save(name, rec)
 
 
-def run_matmul(name, post_softmax, A, B, A_bit, B_bit, H, bs=4, total_memory=None, hcw=True):
+def run_matmul(name, post_softmax, A, B, A_bit, B_bit, H, bs=4, total_memory=None, hcw=True, quantizer='adalog'):
     import quant_layers
     ref_shim.install(total_memory if total_memory is not None else 16 * 2 ** 30)
     kw = dict(A_bit=A_bit, B_bit=B_bit, calib_batch_size=bs, search_round=3, eq_n=128, head_channel_wise=hcw,
               num_heads=H, fpcs=True, steps=6)
     if post_softmax:
-        m = quant_layers.PostSoftmaxAsymmetricallyBatchingQuantMatMul(quantizer='adalog', **kw)
+        m = quant_layers.PostSoftmaxAsymmetricallyBatchingQuantMatMul(quantizer=quantizer, **kw)
     else:
         m = quant_layers.AsymmetricallyBatchingQuantMatMul(**kw)
-    rec = dict(kind=type(m).__name__, cfg=dict(A_bit=A_bit, B_bit=B_bit, H=H, bs=bs, hcw=hcw,
+    rec = dict(kind=type(m).__name__, cfg=dict(A_bit=A_bit, B_bit=B_bit, H=H, bs=bs, hcw=hcw, quantizer=quantizer,
                                               memory=ref_shim._Props.total_memory // 2), A=A.clone(), B=B.clone())
     with torch.no_grad(), TopkTap() as tap:
         m.raw_input = [A, B]
@@ -256,6 +271,26 @@ def main():
 
 
 
+def main_round2():
+    """non-default branches selectable by config string: post-GELU search without
+    FPCS, the fixed-base post-GELU / post-softmax quantizers, the PTQ4ViT twin-uniform baseline"""
+    ref_shim.install()
+    torch.manual_seed(6)
+    xg = torch.nn.functional.gelu(lnlike(8, 10, 48))
+    run_linear('linear_postgelu_nofpcs_w4a4', 'PostGeluLogBasedBatchingQuantLinear', 48, 24, xg, 4, 4, fpcs=False,
+               quantizer='adalog')
+    run_linear('linear_postgelu_log2_w4a4', 'PostGeluLogBasedBatchingQuantLinear', 48, 24, xg, 4, 4, quantizer='log2')
+    run_linear('linear_postgelu_logsqrt2_w3a3', 'PostGeluLogBasedBatchingQuantLinear', 48, 24, xg, 3, 3,
+               quantizer='logsqrt2')
+    run_linear('linear_twin_w4a4', 'PostGeluTwinUniformBatchingQuantLinear', 48, 24, xg, 4, 4)
+    run_linear('linear_twin_nofpcs_w3a3', 'PostGeluTwinUniformBatchingQuantLinear', 48, 24, xg, 3, 3, fpcs=False)
+    p = torch.softmax(torch.randn(8, 2, 10, 10) * 2, dim=-1)
+    v = torch.randn(8, 2, 10, 16) * (1 + torch.arange(2).view(1, 2, 1, 1))
+    run_matmul('matmul_pv_log2_s4a4', True, p, v, 4, 4, 2, quantizer='log2')
+    run_matmul('matmul_pv_logsqrt2_s4a4', True, p, v, 4, 4, 2, quantizer='logsqrt2')
+    run_matmul('matmul_pv_logsqrt2_s6a6', True, p, v, 6, 6, 2, quantizer='logsqrt2')
+
+
 # ------------------------------------------------------------------------------------------------ model level
 def install_fake_timm():
     """Register a minimal `timm` so the reference's utils/wrap_net.py imports: its Attention / WindowAttention
@@ -328,5 +363,7 @@ if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if what in ('layers', 'all'):
         main()
+    if what in ('round2', 'all'):
+        main_round2()
     if what in ('models', 'all'):
         main_models()

@@ -37,6 +37,20 @@ def _lq_from(q):
     return l
 
 
+def _any_q_from(q):
+    """oracle state holder for whatever quantizer object the product hands to a sweep"""
+    name = type(q).__name__
+    if name == 'TwinUniformQuantizer':
+        return O.TQ(q.n_bits, scale=q.scale.detach())
+    if getattr(q, 'is_log', False) and not hasattr(q, 'table2'):
+        sh = getattr(q, 'shift', None)
+        return O.FixedLogQ('log2' if 'Sqrt' not in name else 'logsqrt2', q.n_bits, scale=q.scale.detach(),
+                           shift=None if sh is None else sh.detach(), bias_reparamed=bool(getattr(q, 'bias_reparamed', False)))
+    if getattr(q, 'is_log', False):
+        return _lq_from(q)
+    return _uq_from(q)
+
+
 def _lin(ctx, weight3, bias, w_bit=4, a_bit=4, a_kind='uniform', cw=False):
     n_V = weight3.shape[0]
     s = O.LinearSearch(weight3.detach().reshape(-1, weight3.shape[-1]), None if bias is None else bias.detach(),
@@ -68,7 +82,7 @@ def linear_err_a_self(ctx, cs, cz, n_levels, channel_wise):
 def linear_err_w(ctx, weight3, bias, aq, cs, cz, n_levels_w):
     log = getattr(aq, 'is_log', False)
     s = _lin(ctx, weight3, bias, w_bit=_bits(n_levels_w), a_bit=aq.n_bits, a_kind='adalog' if log else 'uniform')
-    s.aq = _lq_from(aq) if log else _uq_from(aq)
+    s.aq = _any_q_from(aq)
     return _dp(s.sims_w(cs, cz))
 
 
@@ -76,6 +90,14 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a):
     s = _lin(ctx, weight3, bias, w_bit=wq.n_bits, a_bit=_bits(n_levels_a))
     s.wq = _uq_from(wq)
     return _dp(s.sims_a(cs, cz))
+
+
+def linear_err_a_twin(ctx, weight3, bias, wq, s_neg, cands, n_levels):
+    s = _lin(ctx, weight3, bias, w_bit=wq.n_bits, a_bit=_bits(n_levels), a_kind='twin')
+    s.wq = _uq_from(wq)
+    s.aq.scale = torch.stack([torch.zeros_like(s_neg), s_neg.detach()])
+    pad = torch.cat([cands, cands[:, -1:]], dim=-1)          # the oracle (like the reference) drops the last column
+    return _dp(s.sims_a_twin(pad))
 
 
 def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
@@ -102,7 +124,7 @@ def matmul_err_A(ctx, Bq, cs, cz, n_levels_A, hcw):
 def matmul_err_B(ctx, Aq, cs, cz, n_levels_B, hcw):
     log = getattr(Aq, 'is_log', False)
     s = _mm(ctx, Aq.n_bits, _bits(n_levels_B), hcw, post_softmax=log)
-    s.Aq = _lq_from(Aq) if log else _uq_from(Aq)
+    s.Aq = _any_q_from(Aq)
     return _dp(s.sims_B(cs, cz))
 
 
@@ -159,6 +181,7 @@ def install(monkeypatch, bs=4, memory=8 * 2 ** 30):
     Cfg.bs, Cfg.memory = bs, memory
     monkeypatch.setattr(sweep, 'require_cuda', lambda dev: None)
     for name in ('linear_err_w_self', 'linear_err_a_self', 'linear_err_w', 'linear_err_a', 'linear_err_log',
+                 'linear_err_a_twin',
                  'matmul_err_A', 'matmul_err_B', 'matmul_err_A_log_base', 'conv_err_w'):
         monkeypatch.setattr(sweep, name, globals()[name])
     monkeypatch.setattr(sweep, 'ConvCtx', ConvCtx)

@@ -42,7 +42,7 @@ def to_dev(g):
 def build_linear(g, cls, **extra):
     c = g['cfg']
     m = cls(c['in_f'], c['out_f'], bias=c['bias'], w_bit=c['w_bit'], a_bit=c['a_bit'], calib_batch_size=c['bs'],
-            eq_n=128, fpcs=True, steps=6, search_round=3, n_V=c['n_V'], **extra).to(DEV)
+            eq_n=128, fpcs=c.get('fpcs', True), steps=6, search_round=3, n_V=c['n_V'], **extra).to(DEV)
     m.weight.data.copy_(g['weight'])
     if c['bias']:
         m.bias.data.copy_(g['bias'])
@@ -112,6 +112,75 @@ def test_postgelu_forced(name):
     assert torch.equal(m.a_quantizer.scale.data, s.aq.scale) and torch.equal(m.a_quantizer.q, s.aq.q)
     assert torch.equal(m.a_quantizer.table1.cpu(), s.aq.table1.cpu()) and torch.equal(m.a_quantizer.table2.cpu(), s.aq.table2.cpu())
     assert torch.equal(m.w_quantizer.scale.data, s.wq.scale)
+
+
+@pytest.mark.parametrize('name,tmp_kind', [('linear_postgelu_nofpcs_w4a4', None), ('linear_postgelu_log2_w4a4', 'log2'),
+                                           ('linear_postgelu_logsqrt2_w3a3', 'logsqrt2')])
+def test_postgelu_nondefault_forced(name, tmp_kind):
+    """post-GELU search without FPCS (linear.py:816-854, :985-988) and the fixed-base quantizers swapped in after the
+    AdaLog search (:990-994), evaluation by evaluation against the oracle on the same device"""
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    s = oracle_linear(g, a_kind='adalog', fpcs_on=g['cfg']['fpcs'])
+    s.search_postgelu(tmp_kind=tmp_kind)
+    m = build_linear(g, QL.PostGeluLogBasedBatchingQuantLinear, quantizer=g['cfg']['quantizer'])
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(name)
+    assert torch.equal(m.a_quantizer.scale.data, s.aq.scale) and torch.equal(m.w_quantizer.scale.data, s.wq.scale)
+    assert type(m.a_quantizer).__name__ == {None: 'ShiftAdaLogQuantizer', 'log2': 'ShiftLog2Quantizer',
+                                            'logsqrt2': 'ShiftLogSqrt2Quantizer'}[tmp_kind]
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        out = m(g['x'])
+    ref = torch.nn.functional.linear(s.aq(g['x']), O.quant_weight(s.weight, s.wq, s.n_V), s.bias)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('name', ['linear_twin_w4a4', 'linear_twin_nofpcs_w3a3'])
+def test_twin_uniform_forced(name):
+    """PTQ4ViT twin-uniform baseline (linear.py:624-721): the 29-candidate positive-scale sweep runs on the int8
+    tensor-core path with the fixed negative branch folded into the target; the weight sweeps see the twin-quantised
+    activations as three bf16 pieces"""
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    s = oracle_linear(g, a_kind='twin', fpcs_on=g['cfg']['fpcs'])
+    s.search_twin()
+    m = build_linear(g, QL.PostGeluTwinUniformBatchingQuantLinear)
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(name)
+    assert torch.equal(m.a_quantizer.scale.data, s.aq.scale) and torch.equal(m.w_quantizer.scale.data, s.wq.scale)
+    assert torch.equal(m.w_quantizer.zero_point.data, s.wq.zero_point)
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        out = m(g['x'])
+    ref = torch.nn.functional.linear(s.aq(g['x']), O.quant_weight(s.weight, s.wq, s.n_V), s.bias)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('name', ['matmul_pv_log2_s4a4', 'matmul_pv_logsqrt2_s4a4', 'matmul_pv_logsqrt2_s6a6'])
+def test_matmul_fixed_base_forced(name):
+    """post_softmax_quantizer 'log2' / 'logsqrt2' (matmul.py:307-310): the V sweep against a Log2 / LogSqrt2 operand"""
+    from adalog_b200 import quant_layers as QL
+    g = to_dev(load_golden(name))
+    c = g['cfg']
+    s = O.MatMulSearch(g['A'].clone(), g['B'].clone(), g['raw_out'].clone(), c['A_bit'], c['B_bit'], c['H'],
+                       calib_batch_size=c['bs'], head_channel_wise=c['hcw'], post_softmax=True, quantizer=c['quantizer'])
+    s.search()
+    m = QL.PostSoftmaxAsymmetricallyBatchingQuantMatMul(
+        A_bit=c['A_bit'], B_bit=c['B_bit'], calib_batch_size=c['bs'], search_round=3, eq_n=128,
+        head_channel_wise=c['hcw'], num_heads=c['H'], fpcs=True, steps=6, quantizer=c['quantizer']).to(DEV)
+    with torch.no_grad(), ForcedTopk(s.trace.evals) as tap:
+        m.raw_input, m.raw_out = [g['A'].clone(), g['B'].clone()], g['raw_out'].clone()
+        m.hyperparameter_searching()
+    tap.report(name)
+    assert torch.equal(m.B_quantizer.scale.data, s.Bq.scale) and torch.equal(m.B_quantizer.zero_point.data, s.Bq.zero_point)
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        assert torch.equal(m(g['A'], g['B']), s.Aq(g['A']) @ s.Bq(g['B']))
 
 
 @pytest.mark.parametrize('name', MATMUL)

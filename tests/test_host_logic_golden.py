@@ -18,9 +18,11 @@ CONV = ['conv_patch_w4', 'conv_patch_w6']
 
 
 class TopkTap:
-    def __init__(self):
+    def __init__(self, argmax=False):
         self.evals = []
         self._orig = torch.topk
+        self._orig_argmax = torch.Tensor.argmax
+        self._argmax = argmax
 
     def __enter__(self):
         def tapped(inp, k, dim=-1, **kw):
@@ -28,10 +30,20 @@ class TopkTap:
             self.evals.append(dict(sims=inp.detach().clone(), k=k, dim=dim, idx=res[1].clone()))
             return res
         torch.topk = tapped
+        if self._argmax:                     # the twin-uniform search selects with Tensor.argmax (linear.py:691)
+            orig = self._orig_argmax
+
+            def tapped_argmax(t, *a, **kw):
+                res = orig(t, *a, **kw)
+                self.evals.append(dict(sims=t.detach().clone(), k=1, dim=kw.get('dim', a[0] if a else None),
+                                       idx=res.clone(), argmax=True))
+                return res
+            torch.Tensor.argmax = tapped_argmax
         return self
 
     def __exit__(self, *a):
         torch.topk = self._orig
+        torch.Tensor.argmax = self._orig_argmax
 
 
 def assert_trace(gold, got):
@@ -53,7 +65,7 @@ def assert_state(gold_state, module):
 def build_linear(g, cls, **extra):
     c = g['cfg']
     m = cls(c['in_f'], c['out_f'], bias=c['bias'], w_bit=c['w_bit'], a_bit=c['a_bit'], calib_batch_size=c['bs'],
-            eq_n=128, fpcs=True, steps=6, search_round=3, n_V=c['n_V'], **extra)
+            eq_n=128, fpcs=c.get('fpcs', True), steps=6, search_round=3, n_V=c['n_V'], **extra)
     m.weight.data.copy_(g['weight'])
     if c['bias']:
         m.bias.data.copy_(g['bias'])
@@ -112,6 +124,64 @@ def test_postgelu(name, monkeypatch):
         m.reparam_bias()
         assert_state(g['state_bias_reparamed'], m)
         assert torch.equal(m(g['x']), g['quant_out_bias_reparamed'])
+
+
+@pytest.mark.parametrize('name', ['linear_postgelu_nofpcs_w4a4', 'linear_postgelu_log2_w4a4',
+                                  'linear_postgelu_logsqrt2_w3a3'])
+def test_postgelu_nondefault(name, monkeypatch):
+    """fpcs=False driver (linear.py:985-988 with the scale-only search :816-854) and the fixed-base quantizers swapped
+    in after the AdaLog search (:990-994)"""
+    g = load_golden(name)
+    fake.install(monkeypatch, g['cfg']['bs'], g['cfg']['memory'])
+    m = build_linear(g, QL.PostGeluLogBasedBatchingQuantLinear, quantizer=g['cfg']['quantizer'])
+    with torch.no_grad(), TopkTap() as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    assert_trace(g['evals'], tap.evals)
+    assert_state(g['state'], m)
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        assert torch.equal(m(g['x']), g['quant_out'])
+        m.reparam_bias()
+        assert_state(g['state_bias_reparamed'], m)
+        assert torch.equal(m(g['x']), g['quant_out_bias_reparamed'])
+
+
+@pytest.mark.parametrize('name', ['linear_twin_w4a4', 'linear_twin_nofpcs_w3a3'])
+def test_twin_uniform(name, monkeypatch):
+    """PTQ4ViT twin-uniform baseline (linear.py:624-721; post_gelu_quantizer='ptq4vit')"""
+    g = load_golden(name)
+    fake.install(monkeypatch, g['cfg']['bs'], g['cfg']['memory'])
+    m = build_linear(g, QL.PostGeluTwinUniformBatchingQuantLinear)
+    with torch.no_grad(), TopkTap(argmax=True) as tap:
+        m.raw_input, m.raw_out = g['x'].clone(), g['raw_out'].clone()
+        m.hyperparameter_searching()
+    assert_trace(g['evals'], tap.evals)
+    assert [bool(e.get('argmax')) for e in g['evals']] == [bool(e.get('argmax')) for e in tap.evals]
+    assert_state(g['state'], m)
+    assert m.calibrated and not hasattr(m, 'raw_input')
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        assert torch.equal(m(g['x']), g['quant_out'])
+
+
+@pytest.mark.parametrize('name', ['matmul_pv_log2_s4a4', 'matmul_pv_logsqrt2_s4a4', 'matmul_pv_logsqrt2_s6a6'])
+def test_matmul_post_softmax_fixed_base(name, monkeypatch):
+    """post_softmax_quantizer 'log2' / 'logsqrt2' (matmul.py:307-310, :367-375)"""
+    g = load_golden(name)
+    c = g['cfg']
+    fake.install(monkeypatch, c['bs'], c['memory'])
+    m = QL.PostSoftmaxAsymmetricallyBatchingQuantMatMul(
+        A_bit=c['A_bit'], B_bit=c['B_bit'], calib_batch_size=c['bs'], search_round=3, eq_n=128,
+        head_channel_wise=c['hcw'], num_heads=c['H'], fpcs=True, steps=6, quantizer=c['quantizer'])
+    with torch.no_grad(), TopkTap() as tap:
+        m.raw_input, m.raw_out = [g['A'].clone(), g['B'].clone()], g['raw_out'].clone()
+        m.hyperparameter_searching()
+    assert_trace(g['evals'], tap.evals)
+    assert_state(g['state'], m)
+    m.mode = 'quant_forward'
+    with torch.no_grad():
+        assert torch.equal(m(g['A'], g['B']), g['quant_out'])
 
 
 @pytest.mark.parametrize('name', MATMUL)

@@ -120,6 +120,65 @@ def test_conv(name):
     assert torch.equal(torch.nn.functional.conv2d(g['x'], w, s.bias, c['k']), g['quant_out'])
 
 
+GELU_R2 = [('linear_postgelu_nofpcs_w4a4', None), ('linear_postgelu_log2_w4a4', 'log2'),
+           ('linear_postgelu_logsqrt2_w3a3', 'logsqrt2')]
+
+
+@pytest.mark.parametrize('name,tmp_kind', GELU_R2)
+def test_linear_postgelu_nondefault(name, tmp_kind):
+    """linear.py:985-988 (fpcs=False: base search, scale search :816-854, plain weight search) and :990-994 (fixed-base
+    quantizer swapped in after the AdaLog search)"""
+    g = load_golden(name)
+    s = make_linear(g, a_kind='adalog', fpcs_on=g['cfg']['fpcs'])
+    s.search_postgelu(tmp_kind=tmp_kind)
+    assert_trace(g['evals'], s.trace)
+    st = g['state']
+    assert torch.equal(st['w_quantizer.scale'], s.wq.scale)
+    assert torch.equal(st['w_quantizer.zero_point'], s.wq.zero_point)
+    assert torch.equal(st['a_quantizer.scale'], s.aq.scale)
+    if tmp_kind is None:
+        assert torch.equal(st['a_quantizer.q'], s.aq.q)
+    else:
+        assert 'a_quantizer.q' not in st
+    out = torch.nn.functional.linear(s.aq(g['x']), O.quant_weight(s.weight, s.wq, s.n_V), s.bias)
+    assert torch.equal(out, g['quant_out'])
+    s.reparam_bias()
+    assert torch.equal(g['state_bias_reparamed']['bias'], s.bias)
+    out = torch.nn.functional.linear(s.aq(g['x']), O.quant_weight(s.weight, s.wq, s.n_V), s.bias)
+    assert torch.equal(out, g['quant_out_bias_reparamed'])
+
+
+@pytest.mark.parametrize('name', ['linear_twin_w4a4', 'linear_twin_nofpcs_w3a3'])
+def test_linear_twin_uniform(name):
+    """linear.py:624-721: PTQ4ViT twin-uniform baseline (29 power-of-two scales, argmax selection)"""
+    g = load_golden(name)
+    s = make_linear(g, a_kind='twin', fpcs_on=g['cfg']['fpcs'])
+    s.search_twin()
+    assert_trace(g['evals'], s.trace)
+    assert [bool(e.get('argmax')) for e in g['evals']] == [bool(e.get('argmax')) for e in s.trace.evals]
+    st = g['state']
+    assert torch.equal(st['w_quantizer.scale'], s.wq.scale)
+    assert torch.equal(st['w_quantizer.zero_point'], s.wq.zero_point)
+    assert torch.equal(st['a_quantizer.scale'], s.aq.scale)
+    out = torch.nn.functional.linear(s.aq(g['x']), O.quant_weight(s.weight, s.wq, s.n_V), s.bias)
+    assert torch.equal(out, g['quant_out'])
+
+
+@pytest.mark.parametrize('name', ['matmul_pv_log2_s4a4', 'matmul_pv_logsqrt2_s4a4', 'matmul_pv_logsqrt2_s6a6'])
+def test_matmul_post_softmax_fixed_base(name):
+    """matmul.py:307-310, :367-375: Log2 / LogSqrt2 on the softmax operand, one FPCS pass over B"""
+    g = load_golden(name)
+    c = g['cfg']
+    s = O.MatMulSearch(g['A'].clone(), g['B'].clone(), g['raw_out'].clone(), c['A_bit'], c['B_bit'], c['H'],
+                       calib_batch_size=c['bs'], head_channel_wise=c['hcw'], memory=c['memory'], post_softmax=True,
+                       quantizer=c['quantizer'])
+    s.search()
+    assert_trace(g['evals'], s.trace)
+    st = g['state']
+    assert torch.equal(st['B_quantizer.scale'], s.Bq.scale) and torch.equal(st['B_quantizer.zero_point'], s.Bq.zero_point)
+    assert torch.equal(s.Aq(g['A']) @ s.Bq(g['B']), g['quant_out'])
+
+
 def test_quantizer_forwards():
     g = load_golden('quantizers')
     for c in g['cases']:
