@@ -47,6 +47,20 @@ class FusedArgs(ctypes.Structure):
     ]
 
 
+class LinFusedArgs(ctypes.Structure):
+    """mirror of adalog_lin_fused_args"""
+    _fields_ = [
+        ('x', c_vp), ('ldx', c_i64), ('Bm', c_vp), ('b_rows', c_i64),
+        ('K', ctypes.c_int32), ('N', ctypes.c_int32), ('U', ctypes.c_int32),
+        ('P', ctypes.c_int32), ('n_levels', ctypes.c_int32),
+        ('gen', ctypes.c_int32), ('dtype', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('cs', c_vp), ('cz', c_vp), ('cq', c_vp), ('shift', c_vp), ('mtab', c_vp),
+        ('y', c_vp), ('ldy', c_i64),
+        ('rs', c_vp), ('ccs', c_vp), ('ccb', c_vp),
+        ('partial', c_vp),
+    ]
+
+
 # name -> argtypes; every function returns int except adalog_last_error
 SIGNATURES = {
     'adalog_version': [],
@@ -65,6 +79,8 @@ SIGNATURES = {
     'adalog_cand_gemm_err': [ctypes.POINTER(GemmErrArgs), c_vp],
     'adalog_fused_cand_gemm_err_grid': [ctypes.POINTER(FusedArgs)],
     'adalog_fused_cand_gemm_err': [ctypes.POINTER(FusedArgs), c_vp],
+    'adalog_lin_fused_cand_gemm_err_grid': [ctypes.POINTER(LinFusedArgs)],
+    'adalog_lin_fused_cand_gemm_err': [ctypes.POINTER(LinFusedArgs), c_vp],
     'adalog_gemm_dequant': [ctypes.POINTER(GemmErrArgs), c_vp, c_i64, c_i64, c_vp],
     'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
 }
@@ -72,7 +88,8 @@ SIGNATURES = {
 _lib = None
 # kernels launched through this binding (bench.py reports it as gpu_launches)
 LAUNCHES = {'count': 0}
-_NO_LAUNCH = {'adalog_version', 'adalog_cand_gemm_err_grid', 'adalog_fused_cand_gemm_err_grid'}
+_NO_LAUNCH = {'adalog_version', 'adalog_cand_gemm_err_grid', 'adalog_fused_cand_gemm_err_grid',
+              'adalog_lin_fused_cand_gemm_err_grid'}
 
 
 class AdalogError(RuntimeError):

@@ -10,7 +10,7 @@ import threading
 import torch
 
 from . import _lib
-from ._lib import AdalogError, FusedArgs, GemmErrArgs
+from ._lib import AdalogError, FusedArgs, GemmErrArgs, LinFusedArgs
 from ._lib import call as _lib_call
 
 P_TILE = 128   # ADALOG_P
@@ -18,13 +18,14 @@ BK = 64        # ADALOG_BK
 
 # bench.py sets PROFILE['on']: every candidate-GEMM launch is then bracketed by CUDA events on its stream and its
 # algorithmic FLOPs recorded, which is how roofline.achieved is measured live inside the timed region
-PROFILE = {'on': False, 'gemm': [], 'fused': []}
+PROFILE = {'on': False, 'gemm': [], 'fused': [], 'lin': []}
 
 
 def profile_reset(on):
     PROFILE['on'] = bool(on)
     PROFILE['gemm'] = []
     PROFILE['fused'] = []
+    PROFILE['lin'] = []
 
 
 def profile_gemm_summary(split=False):
@@ -390,6 +391,54 @@ def fused_cand_gemm_err(x2d, K, Bm, N, U, UG, brpg, y, ldy, rs, rs_div, rs_mod, 
     else:
         call('adalog_fused_cand_gemm_err', ctypes.byref(a), _stream())
     return partial
+
+
+def lin_fused_cand_gemm_err(x2d, Bm, N, y, rs, ccs, ccb, n_levels, P, cs, cz=None, cq=None, shift=None, mtab=None,
+                            i8=False):
+    """One launch of adalog_lin_fused_cand_gemm_err over all tokens of a linear activation sweep.  Returns the FP64
+    partial [grid, 128], or None when no schedule fits in shared memory (caller: two-kernel path)."""
+    _cuda(x2d, Bm, y, rs, ccs, ccb, cs, cz, cq, shift, mtab)
+    assert x2d.dtype == torch.float32 and x2d.stride(1) == 1 and y.stride(1) == 1
+    log = cq is not None
+    a = LinFusedArgs()
+    a.x, a.ldx = x2d.data_ptr(), int(x2d.stride(0))
+    a.Bm, a.b_rows = Bm.data_ptr(), int(Bm.shape[0])
+    a.K, a.N, a.U = int(x2d.shape[1]), int(N), int(x2d.shape[0])
+    a.P, a.n_levels = int(P), int(n_levels)
+    a.gen, a.dtype = (1 if log else 0), (I8 if i8 else BF16)
+    a.cs = cs.data_ptr()
+    if log:
+        a.cq, a.mtab = cq.data_ptr(), mtab.data_ptr()
+        a.shift = shift.data_ptr() if shift is not None else None
+    else:
+        a.cz = cz.data_ptr()
+    a.y, a.ldy = y.data_ptr(), int(y.stride(0))
+    a.rs, a.ccs, a.ccb = rs.data_ptr(), ccs.data_ptr(), ccb.data_ptr()
+    lib = _lib.load()
+    grid = lib.adalog_lin_fused_cand_gemm_err_grid(ctypes.byref(a))
+    if grid == -3 or grid == -2:
+        return None
+    if grid < 0:
+        raise AdalogError(f'adalog_lin_fused_cand_gemm_err_grid failed ({grid}): {lib.adalog_last_error().decode()}')
+    partial = torch.empty(grid, P_TILE, dtype=torch.float64, device=Bm.device)
+    a.partial = partial.data_ptr()
+    if PROFILE['on']:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call('adalog_lin_fused_cand_gemm_err', ctypes.byref(a), _stream())
+        e1.record()
+        PROFILE['lin'].append((e0, e1, 2.0 * P_TILE * a.U * N * a.K, bool(i8)))
+    else:
+        call('adalog_lin_fused_cand_gemm_err', ctypes.byref(a), _stream())
+    return partial
+
+
+def profile_lin_summary():
+    """{'bf16': (ops, ms, launches), 'i8': (...)} of the fused linear activation sweeps since profile_reset(True)"""
+    torch.cuda.synchronize()
+    def tot(rows):
+        return sum(r[2] for r in rows), sum(r[0].elapsed_time(r[1]) for r in rows), len(rows)
+    return {'bf16': tot([r for r in PROFILE['lin'] if not r[3]]), 'i8': tot([r for r in PROFILE['lin'] if r[3]])}
 
 
 def profile_fused_summary():

@@ -7,6 +7,7 @@ scoring itself is delegated to `score(scales, aux, topk) -> indices`, i.e. to th
 """
 import torch
 
+from .. import _const
 from ..utils import dist as adist
 
 
@@ -27,7 +28,7 @@ def refine(scales, aux, delta, score, axis, new_cnt, width, steps, floor=None):
     best_a = torch.gather(aux, dim=axis, index=idx)
     left = steps - 1
     while left > 0:
-        ramp = torch.linspace(0, 1, steps=new_cnt).to(dev)
+        ramp = _const.linspace01(new_cnt, dev)
         if axis == 0:
             offs = (ramp.view(-1, *([1] * (scales.dim() - 1))) - 0.5) * delta
             delta = delta / (new_cnt - 0.5)
@@ -57,10 +58,10 @@ def percentile_grid(delta_min, delta_max, n_levels, num_zp, num_scale, axis, lea
     """scale x zero-point grid with index p = zp_idx * num_scale + scale_idx
     (linear.py:442-451, :472-481; matmul.py:231-240; conv.py:281-290)."""
     dev = delta_min.device
-    ramp = torch.linspace(0, 1, steps=num_scale).to(dev)
+    ramp = _const.linspace01(num_scale, dev)
     zp_lo = int(n_levels - num_zp / 2)
     zp_hi = int(n_levels + num_zp / 2)
-    zps = torch.tensor(range(zp_lo, zp_hi)).to(dev).repeat_interleave(num_scale)
+    zps = _const.int_range(zp_lo, zp_hi, dev).repeat_interleave(num_scale)
     if axis == 0:
         ones = [1] * lead_dims
         scales = (delta_min + ramp.view(-1, *ones) * (delta_max - delta_min)).repeat(num_zp, *ones) / (2 * n_levels - 1)
@@ -107,7 +108,8 @@ def quantile_pair(x, pct, dim, local=False, seg=None):
     the all-gathered tensor.  seg=(my_segment, n_segments): statistics per group of ranks, returned with a trailing
     segment axis [nq, ..., n_segments]."""
     n = pct.numel()
-    q = torch.cat([pct, 1 - pct]).to(x.device)
+    q = (_const.pct_pair(float(pct[0]), float(pct[1]), x.device) if (n == 2 and not pct.is_cuda)
+         else torch.cat([pct, 1 - pct]).to(x.device))
     if local or not adist.active():
         both = torch.quantile(x, q, dim=dim)
         return both[:n], both[n:]

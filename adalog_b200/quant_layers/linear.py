@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import sweep
+from .. import _const, sweep
 from ..quantizers.uniform import UniformQuantizer, TwinUniformQuantizer
 from ..quantizers.logarithm import ShiftAdaLogQuantizer, ShiftLog2Quantizer, ShiftLogSqrt2Quantizer
 from ..utils import dist as adist
@@ -457,7 +457,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
     def positive_percentile(tensor, q, dim=0):
         """reference linear.py:763-798: rank ceil(count*q)-1 among the positive entries (full sort; the exact
         radix-select replacement is SURVEY.md section 8f rank 2)"""
-        positive = torch.where(tensor > 0, tensor, torch.tensor(float('nan')).to(tensor.device))
+        positive = torch.where(tensor > 0, tensor, torch.full((), float('nan'), device=tensor.device))
         ordered, _ = positive.sort(dim=dim)
         counts = (~torch.isnan(ordered)).sum(dim=dim, keepdim=True).float()
         q = q.reshape(*([q.numel()] + [1] * tensor.ndim))
@@ -484,12 +484,12 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         cache = self._ctx.__dict__.setdefault('_pct_cache', {})
         if ('pos', l, r) not in cache:
             x = self._ctx.x2d.reshape(-1)
-            q = torch.tensor([l, r]).to(x.device)
+            q = _const.floats((l, r), x.device)
             cache[('pos', l, r)] = (self._positive_percentile_dist(x, q) if adist.active()
                                     else self.positive_percentile(x, q))
         cand = cache[('pos', l, r)] + self.a_quantizer.shift.item()
         cand = cand.unsqueeze(0)
-        ramp = torch.tensor([i / (self.eq_n - 1) for i in range(self.eq_n)]).to(cand.device).view(1, -1)
+        ramp = _const.ramp(self.eq_n, cand.device).view(1, -1)
         return cand, cand[:, 0:1] + (cand[:, 1:] - cand[:, 0:1]) * ramp
 
     def _log_scored(self, cs, cq):
@@ -501,7 +501,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
 
     def _q_grid(self):
-        return torch.tensor([i for i in range(10, 11 + self.eq_n)]).to(self.weight.device).view(1, -1)
+        return _const.int_range(10, 11 + self.eq_n, self.weight.device).view(1, -1)
 
     def _search_best_a_scale(self, input_scale_candidates, topk=1):
         """reference linear.py:816-854 (scale-only search at the current base; the fpcs=False path)"""
@@ -539,7 +539,7 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         dev = self.weight.device
         q_all = self._q_grid()
         q_best = self._search_best_log_base(q_all, topk=base_num)
-        ramp = torch.tensor([i / (scale_num - 1) for i in range(scale_num)]).to(dev).view(1, -1)
+        ramp = _const.ramp(scale_num, dev).view(1, -1)
         cs = ud_candidates[:, 0:1] + (ud_candidates[:, 1:] - ud_candidates[:, 0:1]) * ramp
         delta = cs[:, 1:2] - cs[:, 0:1]
         cs = cs.repeat(1, base_num)

@@ -8,7 +8,7 @@ operand, and reduced per (candidate, head) in the epilogue (adalog_b200/sweep.py
 import torch
 from torch import nn
 
-from .. import sweep
+from .. import _const, sweep
 from ..quantizers.uniform import UniformQuantizer
 from ..quantizers.logarithm import Log2Quantizer, LogSqrt2Quantizer, AdaLogQuantizer
 from ..utils import dist as adist
@@ -220,7 +220,7 @@ class PostSoftmaxAsymmetricallyBatchingQuantMatMul(AsymmetricallyBatchingQuantMa
     def _search_best_A_log_base(self, q_candidates=None, topk=1):
         """reference matmul.py:321-358 (bases 10..137; one base for all heads)"""
         if q_candidates is None:
-            q_candidates = torch.tensor([i for i in range(10, 11 + self.eq_n)]).to(self._device()).view(-1, 1, 1, 1, 1)
+            q_candidates = _const.int_range(10, 11 + self.eq_n, self._device()).view(-1, 1, 1, 1, 1)
         nl = self.A_quantizer.n_levels
         parts = [sweep.matmul_err_A_log_base(self._ctx, self.B_quantizer, q_candidates[p0:p1], nl)
                  for p0, p1 in _fpcs.candidate_chunks(self.eq_n)]

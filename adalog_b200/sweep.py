@@ -15,7 +15,7 @@ import os
 
 import torch
 
-from . import ops
+from . import _const, ops
 from .quantizers._ste import flag as _flag
 from .utils import dist as adist
 
@@ -25,6 +25,9 @@ R_BASE = 37.0
 # uniform x uniform sweeps (every quantizer up to 7 bits: |code - zp| <= 127) run on the INT8 tensor cores
 # (tcgen05.mma.kind::i8, S32 accumulation: exact) at twice the bf16 MMA rate and half the operand bytes
 USE_I8 = os.environ.get('ADALOG_B200_I8', '1') == '1'
+
+# linear activation sweeps: generate the candidate operand inside the GEMM kernel (0: generator -> workspace -> GEMM)
+LIN_FUSED = os.environ.get('ADALOG_B200_LIN_FUSED', '1') == '1'
 
 _workspaces = {}
 
@@ -223,9 +226,7 @@ def uniform_operand_params(q):
 
 def search_table_ints(n_levels, device):
     """integer numerators of the 37 live entries of the search LUT (linear.py:750-752 / matmul.py:313-315)."""
-    table = torch.tensor([2 ** (-j / R_BASE) for j in range(120)])
-    table_scale = 1. / (4 * n_levels - 2)
-    return torch.round(table / table_scale)[:37].contiguous().to(device)
+    return _const.search_table_ints(n_levels, device)
 
 
 def linear_err_w_self(weight3, cs, cz, n_levels):
@@ -255,7 +256,7 @@ def _is_adalog(q):
 def _generic_fixed_operand(q, x2d):
     """A fake-quantised tensor with no (integer x one scale) form -- TwinUniform (two scales), Log2 / LogSqrt2 with
     their FP32 sqrt(2) factor and shift -- enters the tensor cores exactly as THREE bf16 pieces of its FP32 value
-    (gen_split3, the patch-embedding trick): fixed operand [x_h | x_m | x_l], candidate operand replicated 3x along K."""
+    (gen_split3, the patch-embedding trick): fixed operand [x_l | x_m | x_h], candidate operand replicated 3x along K."""
     with torch.no_grad():
         return ops.gen_split3(q(x2d))
 
@@ -391,8 +392,14 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a, y2d=None):
     cb = _f32(bias) if bias is not None else torch.zeros(out_f, device=dev)
     ntok = ctx.x2d.shape[0]
     y = ctx.y2d if y2d is None else y2d
-    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, y, out_f, rs, None, 1 << 62, 1, s_w, cb,
-                        k_true=in_f, i8=i8)
+    res = None
+    if LIN_FUSED and out_f % 4 == 0:
+        # candidates generated inside the GEMM kernel: one launch, nothing expanded in HBM (lin_fused_gemm_err.cu)
+        res = ops.lin_fused_cand_gemm_err(ctx.x2d, Bm, out_f, y, rs, s_w.contiguous(), cb.contiguous(), n_levels_a, P,
+                                          c1, cz=z1, i8=i8)
+    if res is None:
+        res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, y, out_f, rs, None, 1 << 62, 1, s_w, cb,
+                            k_true=in_f, i8=i8)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
     return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
 
@@ -438,8 +445,13 @@ def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
     b = _f32(bias).double() if bias is not None else torch.zeros(out_f, device=dev, dtype=torch.float64)
     cb = (b - shift.double() * s_w.double() * colsum.double()).float().contiguous()
     ntok = ctx.x2d.shape[0]
-    res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
-                        k_true=in_f)
+    res = None
+    if LIN_FUSED and out_f % 4 == 0:
+        res = ops.lin_fused_cand_gemm_err(ctx.x2d, Bm, out_f, ctx.y2d, rs, s_w.contiguous(), cb, nl, P, c1, cq=q1,
+                                          shift=shift, mtab=mtab)
+    if res is None:
+        res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
+                            k_true=in_f)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
     return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
 

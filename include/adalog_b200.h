@@ -104,7 +104,8 @@ int adalog_gen_log_fixed(const float* x, int64_t R, int K, int64_t ldx, const fl
                          int kpad, void* stream);
 
 /* fixed operand, unquantised FP32 (conv.py:55-58 with a_bit >= 8): x = h + m + l, three bf16 pieces laid out
- * [R, 3*kpad] so that a krep=3 candidate operand reproduces the FP32 product to 2^-24. */
+ * [R, 3*kpad] as [l | m | h] (smallest first: the tensor core's FP32 accumulator truncates late small addends) so
+ * that a krep=3 candidate operand reproduces the FP32 product to 2^-24. */
 int adalog_gen_split3(const float* x, int64_t R, int K, int64_t ldx, uint16_t* out, int kpad, void* stream);
 
 /* ---------------------------------------------------------------- candidate-batched GEMM + fused error (K5-K10)
@@ -182,6 +183,35 @@ typedef struct {
 /* returns the grid size (so the caller can size `partial`), or negative (e.g. -3: does not fit in shared memory) */
 int adalog_fused_cand_gemm_err_grid(const adalog_fused_args* a);
 int adalog_fused_cand_gemm_err(const adalog_fused_args* a, void* stream);
+
+/* ---------------------------------------------------------------- fused generator + GEMM + error (linear activation sweeps)
+ * replaces: quant_layers/linear.py:394-423 (_search_best_a_scale), :816-854, :856-890, :898-931 (post-GELU AdaLog
+ * scale / base / scale x base searches).  Same arithmetic as adalog_gen_uniform_cand / adalog_gen_log_cand followed by
+ * adalog_cand_gemm_err with column scales, but ONE launch scores all units: persistent CTAs generate each unit's
+ * 128-candidate K-block tiles in shared memory (never in HBM) and multiply them against the whole fixed operand.
+ *
+ * x  [U, K] FP32 (row pitch ldx): the layer input, unit u = token u; candidates are per-tensor:
+ *   gen = ADALOG_GEN_UNIFORM: cs[p], cz[p] (scale, zero point);
+ *   gen = ADALOG_GEN_LOG: cs[p] (scale), cq[p] (base), shift[0] (post-GELU shift or NULL), mtab[37] search-LUT numerators.
+ * Bm [b_rows >= N, KB*64|128]: integer part of the quantised weight (adalog_gen_uniform_fixed), zero padded in K.
+ * yhat[p, n] = rs[p] * ccs[n] * D[p, n];  e[p] += (y[u*ldy + n] - ccb[n] - yhat)^2;  partial[x*128 + p] (FP64), x < grid.
+ * N must be a multiple of 4, ccs 16-byte aligned.  Returns -3 when no schedule fits in shared memory (the caller then
+ * takes the generator -> workspace -> adalog_cand_gemm_err path). */
+typedef struct {
+  const float* x;     int64_t ldx;
+  const void* Bm;     int64_t b_rows;
+  int32_t K;          int32_t N;           int32_t U;
+  int32_t P;          int32_t n_levels;    /* of the candidate-side (activation) quantizer */
+  int32_t gen;        int32_t dtype;       int32_t reserved;
+  const float* cs;    const float* cz;
+  const long long* cq; const float* shift; const float* mtab;
+  const float* y;     int64_t ldy;
+  const float* rs;    const float* ccs;    const float* ccb;
+  double* partial;    /* [grid * 128] */
+} adalog_lin_fused_args;
+
+int adalog_lin_fused_cand_gemm_err_grid(const adalog_lin_fused_args* a);
+int adalog_lin_fused_cand_gemm_err(const adalog_lin_fused_args* a, void* stream);
 
 /* ---------------------------------------------------------------- fake-quant INFERENCE forward of a linear layer
  * replaces: F.linear(Q_a(x), Q_w(W), b) of quant_layers/linear.py:46-51 / :90-92 (quant_forward).

@@ -2,10 +2,11 @@
    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/gpu_dist_check.py
 
 Each rank calibrates the tiny ViT on ITS HALF of the golden's 8 images with the CUDA sweeps (NCCL all-reduce of the
-FP64 per-candidate sums, all-gathered order statistics).  Checks: (1) every rank ends with bit-identical parameters;
-(2) rank 0 then repeats the calibration alone on all 8 images: the sharded result must match it (FP64 sums are
-reassociated across ranks, so equality is expected up to exact-tie-free last-bit effects; reported, and top-1
-agreement asserted)."""
+FP64 per-candidate sums, exact distributed order statistics).  Checks: (1) every rank ends with bit-identical
+parameters; (2) rank 0 then repeats the calibration alone on all images: top-1 agreement asserted, parameters
+identical / total reported for the tiny goldens (4 images = 68 tokens per rank: not whole 32-token slabs) and
+ASSERTED to be all for the BASELINE-sized cases (one DeiT-Tiny W4A4 / DeiT-Small W3A3 block, 32 images per rank),
+where every FP32 partial is shard-invariant by construction."""
 import importlib
 import os
 import sys
@@ -40,8 +41,21 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
-    for name in ('model_vit_test_w4a4', 'model_swin_test_w4a4'):
-        g = torch.load(os.path.join(ROOT, 'tests', 'golden', name + '.pt'), weights_only=False)
+    cases = ['model_vit_test_w4a4', 'model_swin_test_w4a4', 'synthetic:deit_tiny_depth1_patch16_224:4',
+             'synthetic:deit_small_depth1_patch16_224:3']
+    for name in cases:
+        if name.startswith('synthetic:'):
+            # BASELINE-sized layers with 32 images per rank: every shard is a whole number of 32-token slabs, the
+            # condition under which the FP32 partial sums -- and therefore every selected parameter -- must be
+            # IDENTICAL to the single-process run (gemm_err.cu SLAB64, tests/test_gpu_invariance.py)
+            _, mname, bits = name.split(':')
+            torch.manual_seed(5)
+            g = dict(model=mname, bits=int(bits), bs=32, init_state=zoo.create_model(mname).state_dict(),
+                     images=torch.randn(32 * world, 3, 224, 224))
+            must_match = True
+        else:
+            g = torch.load(os.path.join(ROOT, 'tests', 'golden', name + '.pt'), weights_only=False)
+            must_match = False
         images = g['images'].to(dev)
         per = images.shape[0] // world
         model = calibrate(g, images[rank * per:(rank + 1) * per], dev)
@@ -71,6 +85,8 @@ def main():
                   f'quantizer tensors bit-identical, logits rel diff {((a - b).norm() / b.norm()).item():.2e}, '
                   f'top-1 agreement {100 * agree:.1f}%')
             assert same_ranks and agree == 1.0
+            if must_match:
+                assert ident == len(keys), 'shards of whole 32-token slabs must reproduce the single-process result'
         dist.barrier()
     dist.destroy_process_group()
 

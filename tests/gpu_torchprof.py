@@ -42,6 +42,20 @@ for e in prof.events():
         agg[e.name][1] += 1
         lo = e.time_range.start if lo is None else min(lo, e.time_range.start)
         hi = e.time_range.end if hi is None else max(hi, e.time_range.end)
+# GPU busy time = union of all kernel / memcpy intervals (streams overlap); the rest of the span is launch latency and
+# host glue during which no kernel runs
+iv = sorted((e.time_range.start, e.time_range.end) for e in prof.events()
+            if e.device_type == torch.autograd.DeviceType.CUDA)
+busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+for s_, e_ in iv[1:]:
+    if s_ > cur_e:
+        busy += cur_e - cur_s
+        cur_s, cur_e = s_, e_
+    else:
+        cur_e = max(cur_e, e_)
+busy += cur_e - cur_s
+print(f'GPU busy (union of kernel intervals) {busy / 1e6:.3f} s of a span of {(hi - lo) / 1e6:.3f} s = '
+      f'{100 * busy / (hi - lo):.1f}%; {len(iv)} device activities')
 rows = sorted(((t, n, k) for k, (t, n) in agg.items()), reverse=True)
 tot = sum(r[0] for r in rows)
 print(f'sum of GPU kernel+memcpy durations {tot / 1e6:.3f} s over a GPU span of {(hi - lo) / 1e6:.3f} s '
