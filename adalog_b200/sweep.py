@@ -29,6 +29,24 @@ USE_I8 = os.environ.get('ADALOG_B200_I8', '1') == '1'
 # linear activation sweeps: generate the candidate operand inside the GEMM kernel (0: generator -> workspace -> GEMM)
 LIN_FUSED = os.environ.get('ADALOG_B200_LIN_FUSED', '1') == '1'
 
+
+def _use_lin_fused(K, N, log, i8):
+    """Which path scores a linear activation sweep.  Measured on 128 x 197 tokens (tests/gpu_lin_bench.py, fused vs
+    generator -> workspace -> GEMM, ms per evaluation): DeiT-S K=384 int8: N=1152 2.00 vs 2.16, N=1536 2.31 vs 2.36,
+    N=384 1.26 vs 1.17; AdaLog K=1536 N=384 5.1 vs 5.5 (7.7 inside a calibration, where the two kernels of one
+    evaluation overlap less than in a back-to-back loop).  DeiT-B K=768 int8: 5.6 vs 4.8 / 7.9 vs 6.1 and AdaLog K=3072
+    N=768 (two passes that regenerate the operand) 20.5 vs 17.5: with six or more K blocks resident per unit the
+    producers cannot run ahead of the MMAs (one spare stage), and the fixed-operand stream has 3 x 32 KB in flight
+    against 4 x 48 KB of the two-kernel GEMM.  ADALOG_B200_LIN_FUSED=force takes the fused kernel wherever it fits."""
+    mode = os.environ.get('ADALOG_B200_LIN_FUSED', '1')
+    if not LIN_FUSED or mode == '0':
+        return False
+    if mode == 'force':
+        return True
+    if log:
+        return N <= 512                       # one pass: the operand is generated once per unit
+    return (K if i8 else 2 * K) <= 512        # at most four K blocks resident per unit
+
 _workspaces = {}
 
 
@@ -393,7 +411,7 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a, y2d=None):
     ntok = ctx.x2d.shape[0]
     y = ctx.y2d if y2d is None else y2d
     res = None
-    if LIN_FUSED and out_f % 4 == 0:
+    if out_f % 4 == 0 and _use_lin_fused(in_f, out_f, False, i8):
         # candidates generated inside the GEMM kernel: one launch, nothing expanded in HBM (lin_fused_gemm_err.cu)
         res = ops.lin_fused_cand_gemm_err(ctx.x2d, Bm, out_f, y, rs, s_w.contiguous(), cb.contiguous(), n_levels_a, P,
                                           c1, cz=z1, i8=i8)
@@ -446,7 +464,7 @@ def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
     cb = (b - shift.double() * s_w.double() * colsum.double()).float().contiguous()
     ntok = ctx.x2d.shape[0]
     res = None
-    if LIN_FUSED and out_f % 4 == 0:
+    if out_f % 4 == 0 and _use_lin_fused(in_f, out_f, True, False):
         res = ops.lin_fused_cand_gemm_err(ctx.x2d, Bm, out_f, ctx.y2d, rs, s_w.contiguous(), cb, nl, P, c1, cq=q1,
                                           shift=shift, mtab=mtab)
     if res is None:

@@ -9,6 +9,11 @@ the per-candidate FP64 error sums are all-reduced (NCCL), so N ranks calibrate o
   python bench.py [--gpus N --steps K --warmup W]          our arm (CUDA kernels through libadalog_b200.so)
   python bench.py --impl reference [...]                    reference arm: the oracle port of the reference's own
                                                             CPU path on the host cores (bounded sample per step)
+  python bench.py --config {1..5} [...]                     BASELINE.json configs[i-1]: 1 DeiT-T W4A4 / 32 images,
+                                                            2 DeiT-S W3A3 / 128 per GPU (default, weak scaling),
+                                                            3 ViT-B W4A4 / 512 images in total (strong scaling),
+                                                            4 DeiT-B W4A4 / 1024 in total (headline), 5 Swin-B W6A6 / 1024
+  With --gpus 8 and the default config the line also carries a `headline` record: one calibration of config 4.
 
 Prints ONE JSON line (rank 0).  `value` = candidate scorings per second with the images resident in HBM;
 `e2e` = the same through the public API starting from pinned host images (H2D inside the timed region) and ending
@@ -37,13 +42,25 @@ MODEL_ALIASES = {'deit_tiny': 'deit_tiny_patch16_224', 'deit_small': 'deit_small
 DIMS = {'deit_tiny': (192, 3, 12), 'deit_small': (384, 6, 12), 'deit_base': (768, 12, 12), 'vit_base': (768, 12, 12),
         'vit_small': (384, 6, 12)}
 TOKENS = 197
-# dram__bytes_read.sum + dram__bytes_write.sum of one cand_gemm_err_kernel launch from the `ncu --set full` capture in
-# profiles/r1_ncu_full_cand_gemm_err_v2.json (a 1365-unit chunk of a K=3072, N=768 activation sweep: 1.074e9 B of
-# candidate operand + 4.7e6 B of fixed operand are the algorithmic bytes of that launch)
-NCU_TRAFFIC_BYTES = 1.087e9
-NCU_TRAFFIC_NOTE = ('per launch, ncu --set full of a K=3072 N=768 activation-sweep chunk (profiles/'
-                    'r1_ncu_full_cand_gemm_err_v2.json): 1.083 GB read + 4 MB written vs 1.079 GB algorithmic; tensor '
-                    'pipe 93% active in that launch')
+# BASELINE.json configs: (model, bits, images in total or per GPU, scaling)
+CONFIGS = {1: ('deit_tiny', 4, 32, 'weak'), 2: ('deit_small', 3, 128, 'weak'), 3: ('vit_base', 4, 512, 'strong'),
+           4: ('deit_base', 4, 1024, 'strong'), 5: ('swin_base', 6, 1024, 'strong')}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+    summary (profiles/), or None: a bench run cannot measure DRAM traffic itself (never a number taken under a profiler)"""
+    for name in ('r2_ncu_full_lin_fused.json', 'r1_ncu_full_cand_gemm_err_v2.json'):
+        path = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(path):
+            try:
+                d = json.load(open(path))
+                t = d.get('dram_bytes_per_launch')
+                if t:
+                    return float(t), f"profiles/{name}: {d.get('what', '')}"[:300]
+            except Exception:  # noqa: BLE001
+                pass
+    return None, 'no ncu summary with dram_bytes_per_launch under profiles/'
 
 
 def parse():
@@ -52,12 +69,24 @@ def parse():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--model', default='deit_small')
-    ap.add_argument('--bits', type=int, default=3)
-    ap.add_argument('--images-per-gpu', type=int, default=128)
+    ap.add_argument('--config', type=int, default=None, choices=sorted(CONFIGS))
+    ap.add_argument('--model', default=None)
+    ap.add_argument('--bits', type=int, default=None)
+    ap.add_argument('--images-per-gpu', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    return ap.parse_args()
+    ap.add_argument('--no-parity', action='store_true', help='skip the free-running parity / gpu_reference checker leg')
+    ap.add_argument('--no-headline', action='store_true')
+    a = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    model, bits, images, scaling = CONFIGS[a.config or 2]
+    a.scaling = scaling if a.images_per_gpu is None else 'weak'
+    a.model = a.model or model
+    a.bits = a.bits or bits
+    if a.images_per_gpu is None:
+        a.images_per_gpu = images if scaling == 'weak' else max(1, images // world)
+    a.images_total = a.images_per_gpu * world
+    return a
 
 
 def load_peaks():
@@ -66,6 +95,16 @@ def load_peaks():
         p = json.load(open(path))
         return dict(tflops=p.get('bf16_tflops_sustained', p.get('bf16_tflops')), hbm=p.get('hbm_gbs'), src='measured')
     return dict(tflops=1400.0, hbm=6650.0, src='fallback')   # B200_PROFILING.md fallback (sustained)
+
+
+def count_evals(model):
+    """search evaluations of one calibration, from the wrapped model's module classes:
+    plain asymmetric linear 48, channel-wise linear 6 + 48, post-GELU linear 6 + 3 x 13, Q.K^T 36, post-softmax P.V 21,
+    patch-embedding conv 6"""
+    per = {'AsymmetricallyBatchingQuantLinear': 48, 'AsymmetricallyChannelWiseBatchingQuantLinear': 54,
+           'PostGeluLogBasedBatchingQuantLinear': 45, 'AsymmetricallyBatchingQuantMatMul': 36,
+           'PostSoftmaxAsymmetricallyBatchingQuantMatMul': 21, 'AsymmetricallyBatchingQuantConv2d': 6}
+    return sum(per.get(type(m).__name__, 0) for m in model.modules())
 
 
 def model_eval_counts(model_key):
@@ -77,39 +116,104 @@ def model_eval_counts(model_key):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(model_key, bits, n_img, threads):
-    """Bounded sample of the reference's CPU path (oracle port): one weight-search and one activation-search
-    evaluation (2 x 128 candidates) of blocks.0.attn.proj on n_img synthetic images.  Returns (seconds, candidates,
-    MACs per token per candidate of the sample)."""
+def eval_counts_per_block():
+    """search evaluations of one ViT/DeiT block by sweep type (258 in total)"""
+    return {
+        'qkv.a_self_cw': 6, 'qkv.w_self': 6, 'qkv.a_self': 6, 'qkv.w': 18, 'qkv.a': 18,
+        'proj.w_self': 6, 'proj.a_self': 6, 'proj.w': 18, 'proj.a': 18,
+        'fc1.a_self_cw': 6, 'fc1.w_self': 6, 'fc1.a_self': 6, 'fc1.w': 18, 'fc1.a': 18,
+        'fc2.w_self': 6, 'fc2.log': 21, 'fc2.w': 18,
+        'matmul1.A': 18, 'matmul1.B': 18, 'matmul2.log_base': 3, 'matmul2.B': 18,
+    }
+
+
+def cpu_stratified_sample(model_key, bits, n_img, threads):
+    """Bounded, STRATIFIED sample of the reference's CPU path (oracle port): ONE evaluation (128 candidates) of every
+    sweep type of a transformer block -- weight / activation / self-error searches of qkv, proj, fc1, fc2 (post-GELU
+    AdaLog), Q.K^T operand searches, the post-softmax base search and the V search -- on n_img synthetic images at the
+    model's real layer sizes.  The seconds of each type are weighted by how often a calibration runs it
+    (eval_counts_per_block x depth) and scaled linearly from n_img to the bench's images (every sweep is a sum over
+    samples).  Returns (estimated seconds of a full calibration per image, image-independent seconds, per-type seconds)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import adalog_oracle as O
     torch.set_num_threads(threads)
-    D = DIMS[model_key][0]
-    g = torch.Generator().manual_seed(5)
-    x = torch.randn(n_img, TOKENS, D, generator=g) * (torch.rand(D, generator=g) * 2) + 0.3 * torch.randn(D, generator=g)
-    W = torch.nn.init.trunc_normal_(torch.empty(D, D), std=.02, generator=g)
-    b = torch.zeros(D)
-    y = torch.nn.functional.linear(x, W, b)
-    s = O.LinearSearch(W, b, x, y, bits, bits, calib_batch_size=32)
-    s.init_calib()
+    D, H, depth = DIMS[model_key]
     nl = 2 ** (bits - 1)
-    wcs, wcz = O.weight_candidates(W, 1, nl, 128)
-    acs, acz = O.activation_candidates(x, nl, 128, False)
-    s.wq.scale, s.wq.zero_point = wcs[64].clone(), wcz[64].clone().float()
-    s.aq.scale, s.aq.zero_point = acs[:, 64].clone(), acz[:, 64].clone().float()
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        s.sims_w(wcs, wcz)
-        s.sims_a(acs, acz)
-    return time.perf_counter() - t0, 256, float(D * D)
+    g = torch.Generator().manual_seed(5)
+
+    def lnlike(n, c):
+        return torch.randn(n_img, TOKENS, c, generator=g) * (torch.rand(c, generator=g) * 2) + 0.3 * torch.randn(c, generator=g)
+
+    t = {}
+
+    def clock(name, fn):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            fn()
+        t[name] = time.perf_counter() - t0
+
+    for name, in_f, out_f, n_V in (('qkv', D, 3 * D, 3), ('proj', D, D, 1), ('fc1', D, 4 * D, 1), ('fc2', 4 * D, D, 1)):
+        log = name == 'fc2'
+        x = torch.nn.functional.gelu(lnlike(n_img, in_f)) if log else lnlike(n_img, in_f)
+        W = torch.nn.init.trunc_normal_(torch.empty(out_f, in_f), std=.02, generator=g)
+        b = torch.zeros(out_f)
+        y = torch.nn.functional.linear(x, W, b)
+        s = O.LinearSearch(W, b, x, y, bits, bits, n_V=n_V, calib_batch_size=32, a_kind='adalog' if log else 'uniform')
+        s.init_calib()
+        wcs, wcz = O.weight_candidates(W, n_V, nl, 128)
+        s.wq.scale, s.wq.zero_point = wcs[64].clone(), wcz[64].clone().float()
+        if log:
+            ud, sc = O.postgelu_candidates(x, O.SHIFT_GELU, 128)
+            s.aq.scale = sc[:, -2].clone()
+            s.aq.update_table()
+            qc = torch.arange(10, 138).view(1, -1)
+            clock('fc2.log', lambda: s.sims_log(sc, qc))
+        else:
+            acs, acz = O.activation_candidates(x, nl, 128, False)
+            s.aq.scale, s.aq.zero_point = acs[:, 64].clone(), acz[:, 64].clone().float()
+            clock(name + '.a', lambda: s.sims_a(acs, acz))
+            clock(name + '.a_self', lambda: s.sims_a_self(acs, acz))
+            if name in ('qkv', 'fc1'):
+                ccs, ccz = O.activation_candidates(x, nl, 128, True)
+                s.a_channel_wise = True
+                clock(name + '.a_self_cw', lambda: s.sims_a_self(ccs, ccz))
+                s.a_channel_wise = False
+        clock(name + '.w', lambda: s.sims_w(wcs, wcz))
+        clock(name + '.w_self', lambda: s.sims_w_self(wcs, wcz))
+    dh = D // H
+    q = torch.randn(n_img, H, TOKENS, dh, generator=g)
+    k = torch.randn(n_img, H, dh, TOKENS, generator=g)
+    m = O.MatMulSearch(q, k, q @ k, bits, bits, H, calib_batch_size=32)
+    m.init_calib()
+    cs, cz = O.matmul_candidates(q, nl, 128, True)
+    kcs, kcz = O.matmul_candidates(k, nl, 128, True)
+    m.Aq.scale, m.Aq.zero_point = cs[-2].clone(), cz[-2].clone().float()
+    m.Bq.scale, m.Bq.zero_point = kcs[-2].clone(), kcz[-2].clone().float()
+    clock('matmul1.A', lambda: m.sims_A(cs, cz))
+    clock('matmul1.B', lambda: m.sims_B(kcs, kcz))
+    pr = torch.softmax(torch.randn(n_img, H, TOKENS, TOKENS, generator=g) * 2, dim=-1)
+    v = torch.randn(n_img, H, TOKENS, dh, generator=g)
+    m2 = O.MatMulSearch(pr, v, pr @ v, bits, bits, H, calib_batch_size=32, post_softmax=True)
+    m2.init_calib()
+    vcs, vcz = O.matmul_candidates(v, nl, 128, True)
+    m2.Bq.scale, m2.Bq.zero_point = vcs[-2].clone(), vcz[-2].clone().float()
+    clock('matmul2.log_base', lambda: m2.sims_A_log_base(torch.arange(10, 138).view(-1, 1, 1, 1, 1)))
+    clock('matmul2.B', lambda: m2.sims_B(vcs, vcz))
+    counts = eval_counts_per_block()
+    # the weight self-error sweeps touch no calibration sample: their seconds do not scale with the image count
+    per_image_block = sum(counts[k_] * t[k_] for k_ in counts if not k_.endswith('.w_self')) / n_img
+    fixed_block = sum(counts[k_] * t[k_] for k_ in counts if k_.endswith('.w_self'))
+    return per_image_block * depth, fixed_block * depth, t
 
 
 def cpu_arm_value(model_key, bits, n_img, images_per_gpu, threads):
-    """candidates/s in the bench's unit (one candidate scored on `images_per_gpu` images at the model-average cost)"""
-    secs, cands, macs_sample = cpu_sample(model_key, bits, n_img, threads)
-    _, _, macs_avg = model_eval_counts(model_key)
-    norm = (n_img / images_per_gpu) * (macs_sample / macs_avg)
-    return cands * norm / secs, secs, cands
+    """(candidates/s in the bench's unit, seconds the sample took, candidates it scored, per-type seconds)"""
+    t0 = time.perf_counter()
+    per_image, fixed, per_type = cpu_stratified_sample(model_key, bits, n_img, threads)
+    secs = time.perf_counter() - t0
+    evals, cands, _ = model_eval_counts(model_key)
+    est_calibration_s = per_image * images_per_gpu + fixed   # blocks only: patch embedding (6) and head (48) are < 1%
+    return cands / est_calibration_s, secs, 128 * len(per_type), per_type
 
 
 def run_reference(args):
@@ -117,21 +221,21 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_img = 32
-    for _ in range(args.warmup):
-        cpu_arm_value(args.model, args.bits, n_img, args.images_per_gpu, threads)
+    n_img = 4
+    for _ in range(min(args.warmup, 1)):
+        cpu_arm_value(args.model, args.bits, 2, args.images_per_gpu, threads)
     vals, secs_all = [], []
     for _ in range(args.steps):
-        v, secs, cands = cpu_arm_value(args.model, args.bits, n_img, args.images_per_gpu, threads)
+        v, secs, cands, _ = cpu_arm_value(args.model, args.bits, n_img, args.images_per_gpu, threads)
         vals.append(v)
         secs_all.append(secs)
     value = statistics.mean(vals)
-    sample = (f'oracle port of the reference CPU path, {threads} threads: per step 1 weight-search + 1 activation-search '
-              f'evaluation (2x128 candidates) of blocks.0.attn.proj ({args.model}, W{args.bits}A{args.bits}) on {n_img} '
-              f'images; normalised to the bench unit (one candidate on {args.images_per_gpu} images at the '
-              f'model-average GEMM cost per candidate)')
+    sample = (f'oracle port of the reference CPU path, {threads} threads: per step ONE evaluation (128 candidates) of each '
+              f'of the 21 sweep types of a {args.model} W{args.bits}A{args.bits} block on {n_img} images at the real layer '
+              f'sizes; per-type seconds weighted by their count in a calibration (258 per block x depth) and scaled '
+              f'linearly to {args.images_per_gpu} images (every sweep is a sum over samples)')
     out = dict(metric='fpcs_candidates_per_s', value=value, unit='candidates/s', n_gpus=args.gpus, steps=args.steps,
-               warmup=args.warmup, ms_per_step=1e3 * statistics.mean(secs_all), higher_is_better=True, scaling='weak',
+               warmup=args.warmup, ms_per_step=1e3 * statistics.mean(secs_all), higher_is_better=True, scaling=args.scaling,
                vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                config=workload_config(args),
                cpu_baseline=dict(value=value, unit='candidates/s', cores=threads, kind='port', sample=sample),
@@ -142,7 +246,9 @@ def run_reference(args):
 def workload_config(args):
     return dict(workload=f'{args.model} W{args.bits}A{args.bits} FPCS calibration (eq_n=128, steps=6, search_round=3), '
                          f'{args.images_per_gpu} synthetic 224x224 images per GPU, random-init weights, seed 5',
-                images_per_gpu=args.images_per_gpu, l2='inputs larger than L2 + 256 MiB L2 flush between steps',
+                baseline_config=args.config or 2, images_per_gpu=args.images_per_gpu,
+                images_total=args.images_per_gpu * args.gpus,
+                l2='inputs larger than L2 + 256 MiB L2 flush between steps',
                 parallelism=f'dp{args.gpus} (samples sharded, FP64 error sums all-reduced)')
 
 
@@ -224,14 +330,6 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()   # fail loudly if the extension is missing
 
-    cfg = importlib.import_module(f'adalog_b200.configs.{args.bits}bit').Config()
-    cfg.calib_size, cfg.calib_batch_size = args.images_per_gpu, 32
-    model_name = MODEL_ALIASES[args.model]
-    base = build_wrapped(model_name, cfg, dev)
-    g = torch.Generator().manual_seed(5 + 1000 * rank)
-    img = 32 if args.model == 'vit_test' else 224
-    host_images = torch.randn(args.images_per_gpu, 3, img, img, generator=g).pin_memory()
-    dev_images = host_images.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -239,27 +337,40 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(from_host):
-        model = copy.deepcopy(base)
-        flush.fill_(1)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record()
-        images = host_images.to(dev, non_blocking=True) if from_host else dev_images
-        calibrate(model, images, 32)
-        d2h = 0
-        if from_host:
-            _, d2h = quant_params_to_host(model)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        wall = (time.perf_counter() - t0) * 1e3
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms, wall, d2h, model
+    def make_stepper(model_key, bits, images_per_gpu):
+        """(one_step(from_host) -> (ms, wall_ms, d2h_bytes, model), host images, device images, evaluations)"""
+        cfg = importlib.import_module(f'adalog_b200.configs.{bits}bit').Config()
+        cfg.calib_size, cfg.calib_batch_size = images_per_gpu, 32
+        base = build_wrapped(MODEL_ALIASES[model_key], cfg, dev)
+        g = torch.Generator().manual_seed(5 + 1000 * rank)
+        img = 32 if model_key == 'vit_test' else 224
+        host_images = torch.randn(images_per_gpu, 3, img, img, generator=g).pin_memory()
+        dev_images = host_images.to(dev)
+
+        def one_step(from_host):
+            model = copy.deepcopy(base)
+            flush.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            images = host_images.to(dev, non_blocking=True) if from_host else dev_images
+            calibrate(model, images, 32)
+            d2h = 0
+            if from_host:
+                _, d2h = quant_params_to_host(model)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            wall = (time.perf_counter() - t0) * 1e3
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.item()
+            return ms, wall, d2h, model
+        return one_step, host_images, dev_images, count_evals(base)
+
+    one_step, host_images, dev_images, evals = make_stepper(args.model, args.bits, args.images_per_gpu)
 
     for _ in range(args.warmup):
         one_step(False)
@@ -272,10 +383,12 @@ def run_ours(args):
     for _ in range(args.steps):
         ms, wall, _, model = one_step(False)
         times.append(ms)
-    gemm_flops, gemm_ms, gemm_launches = ops.profile_gemm_summary()
-    gemm_split = ops.profile_gemm_summary(split=True)
+    gemm_split = ops.profile_gemm_summary(split=True)          # cand_gemm_err_kernel (W-side, conv, chunked A-side)
+    lin_split = ops.profile_lin_summary()                      # lin_fused_kernel (A-side sweeps of the linear layers)
     fz_flops, fz_ms, fz_launches = ops.profile_fused_summary()
     ops.profile_reset(False)
+    gemm_ms = sum(v[1] for v in gemm_split.values()) + sum(v[1] for v in lin_split.values())
+    gemm_launches = sum(v[2] for v in gemm_split.values()) + sum(v[2] for v in lin_split.values())
     launches = _lib.LAUNCHES['count']
     clocks = sampler.stop() if sampler else None
 
@@ -339,31 +452,81 @@ def run_ours(args):
                          'amplify such rounding-level differences through 12 blocks of 3-bit rounding, so the '
                          'agreement figures here measure that sensitivity, not an error of either path')
 
+    # ---- headline sub-record (BASELINE config 4: DeiT-B W4A4, 1024 images on 8 GPUs) when run on 8 GPUs
+    headline = None
+    if world == 8 and (args.config or 2) == 2 and not args.no_headline:
+        hm, hb, himg = CONFIGS[4][0], CONFIGS[4][1], CONFIGS[4][2] // world
+        h_step, _, _, h_evals = make_stepper(hm, hb, himg)
+        h_sampler = ClockSampler(local) if rank == 0 else None
+        h_ms, h_wall, _, h_model = h_step(False)
+        h_clocks = h_sampler.stop() if h_sampler else None
+        del h_model
+        headline = dict(workload=f'{hm} W{hb}A{hb} FPCS calibration, {himg * world} synthetic images on {world} GPUs '
+                                 f'({himg} per GPU), one calibration, no warm-up of its own',
+                        baseline_config=4, calibration_wall_s=h_ms / 1e3, evaluations=h_evals,
+                        candidates_per_s=128 * h_evals / (h_ms / 1e3), host_wall_s=h_wall / 1e3, clocks=h_clocks)
+
+    # ---- checker leg (rank 0, one GPU): free-running parity against the reference-on-GPU, and its timing
+    parity = gpu_reference = None
+    if rank == 0 and world == 1 and not args.no_parity and (args.config or 2) in (1, 2) and args.model in ('deit_tiny', 'deit_small'):
+        for pth in (os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+            if pth not in sys.path:
+                sys.path.insert(0, pth)
+        from gpu_parity import run_parity
+        slice_model = 'deit_tiny_patch16_224' if args.model == 'deit_tiny' else 'deit_small_depth1_patch16_224'
+        rec = run_parity(slice_model, args.bits, args.images_per_gpu, with_ref64=False, log=lambda *_: None)
+        parity = {k: rec[k] for k in (
+            'model', 'bits', 'images', 'evaluations', 'forced_max_rel_diff', 'forced_max_rel_diff_patch_embed',
+            'evaluations_over_1e5', 'evaluations_over_1e5_unexcused', 'forced_checkpoint_bit_identical',
+            'forced_logits_bit_identical', 'topk_sets_differing', 'topk_sets_differing_outside_reference_noise',
+            'worst_gap_over_reference_noise', 'exact_ties_in_reference', 'exact_ties_preserved',
+            'free_running_quantizer_tensors_identical', 'quantizer_tensors_total', 'free_running_top1_agreement',
+            'probe_images')}
+        parity['what'] = ('tests/gpu_parity.py: oracle (pinned to the unmodified reference) on this GPU vs the CUDA sweeps, '
+                          'teacher-forced (scores, ties, checkpoint) and free running (tensors identical, top-1); '
+                          'patch embedding + block 0 + head of the bench model' if 'depth1' in slice_model else
+                          'tests/gpu_parity.py on the whole model')
+        parity['accuracy_vs_fp64_by_sweep'] = {k: dict(product=v['product_vs_fp64'], reference_fp32=v['ref32_vs_fp64'])
+                                                for k, v in rec['by_sweep'].items()}
+        gpu_reference = dict(kind='oracle port of the reference on the same B200 (torch-CUDA, FP32 like the reference; '
+                                  'each evaluation additionally re-scored in FP64 for the noise measurement)',
+                             model=slice_model, evaluations=rec['evaluations'], seconds=rec['reference_on_gpu_seconds'],
+                             candidates_per_s=128 * rec['evaluations'] / rec['reference_on_gpu_seconds'],
+                             product_seconds_same_slice=rec['product_seconds'],
+                             product_candidates_per_s=128 * rec['evaluations'] / rec['product_seconds'])
+
     if rank == 0:
-        evals, cands, macs_avg = model_eval_counts(args.model) if args.model in DIMS else (0, 0, 0.0)
+        cands = 128 * evals
         ms_step = statistics.mean(times)
         value = world * cands / (ms_step / 1e3)
         peaks = load_peaks()
         # int8 MMAs (tcgen05 kind::i8) run at twice the bf16 rate and MEASURED_PEAKS.json holds a bf16 peak only, so an
         # int8 operation counts as half a bf16 FLOP: `achieved` is bf16-equivalent TFLOP/s = tensor-pipe occupancy x peak
-        bf, i8 = gemm_split['bf16'], gemm_split['i8']
-        achieved = (bf[0] + 0.5 * i8[0]) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-        by_type = {k: dict(launches=v[2], kernel_ms_per_step=v[1] / max(1, args.steps),
-                           tera_ops_per_s=(v[0] / (v[1] / 1e3) / 1e12 if v[1] > 0 else 0.0))
-                   for k, v in gemm_split.items()}
+        bf_ops = gemm_split['bf16'][0] + lin_split['bf16'][0]
+        i8_ops = gemm_split['i8'][0] + lin_split['i8'][0]
+        achieved = (bf_ops + 0.5 * i8_ops) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+
+        def per_type(d):
+            return {k: dict(launches=v[2], kernel_ms_per_step=v[1] / max(1, args.steps),
+                            tera_ops_per_s=(v[0] / (v[1] / 1e3) / 1e12 if v[1] > 0 else 0.0)) for k, v in d.items()}
+        traffic, traffic_note = ncu_traffic()
         out = dict(metric='fpcs_candidates_per_s', value=value, unit='candidates/s', n_gpus=world, steps=args.steps,
-                   warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
+                   warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                    dtype='int8 + bf16 operands holding exact integers (s32 / f32 accumulate), f64 error sums', data='synthetic',
                    config=workload_config(args), evaluations_per_step=evals, candidates_per_step=cands,
                    calibration_wall_s=ms_step / 1e3, fakequant_img_per_s=fq_img_s, fakequant_forward=fq_extra,
                    gpu_launches=launches, clocks=clocks,
-                   roofline=dict(kernel='cand_gemm_err_kernel (tcgen05 candidate GEMM + fused error epilogue)',
+                   roofline=dict(kernel='candidate GEMMs with fused error epilogue: cand_gemm_err_kernel (weight-side / '
+                                        'conv sweeps) + lin_fused_kernel (activation-side sweeps, candidates generated '
+                                        'in shared memory); both tcgen05 + TMEM + TMA',
                                  bound='tensor', achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s',
-                                 frac=achieved / peaks['tflops'] if peaks['tflops'] else None, traffic=NCU_TRAFFIC_BYTES,
-                                 traffic_note=NCU_TRAFFIC_NOTE,
+                                 frac=achieved / peaks['tflops'] if peaks['tflops'] else None, traffic=traffic,
+                                 traffic_note=traffic_note,
                                  peak_source=f"{peaks['src']} bf16_tflops_sustained",
-                                 note='achieved = bf16-equivalent TFLOP/s (an int8 op counts 1/2: kind::i8 runs at 2x '
-                                      'the bf16 rate; the measured peak is bf16)', by_operand_type=by_type,
+                                 note='achieved = algorithmic 2*128*units*N*K ops of every launch / CUDA-event time of '
+                                      'the launches inside the timed steps, in bf16-equivalent TFLOP/s (an int8 op '
+                                      'counts 1/2: kind::i8 runs at 2x the bf16 rate; the measured peak is bf16)',
+                                 cand_gemm_err_kernel=per_type(gemm_split), lin_fused_kernel=per_type(lin_split),
                                  launches=gemm_launches, kernel_ms_per_step=gemm_ms / max(1, args.steps),
                                  share_of_step=gemm_ms / max(1e-9, sum(times)),
                                  other_kernels=[dict(
@@ -377,14 +540,21 @@ def run_ours(args):
             out['e2e'] = dict(value=world * cands / (e2e_ms / 1e3), unit='candidates/s',
                               h2d_bytes_per_step=host_images.numel() * 4, d2h_bytes_per_step=d2h,
                               ms_per_step=e2e_ms)
+        if headline is not None:
+            out['headline'] = headline
+        if parity is not None:
+            out['parity'] = parity
+            out['gpu_reference'] = gpu_reference
         if not args.no_cpu_baseline and world == 1 and args.model in DIMS:
             threads = os.cpu_count() or 1
-            v, secs, c = cpu_arm_value(args.model, args.bits, 64, args.images_per_gpu, threads)
+            v, secs, c, per_type_s = cpu_arm_value(args.model, args.bits, 8, args.images_per_gpu, threads)
             out['cpu_baseline'] = dict(
                 value=v, unit='candidates/s', cores=threads, kind='port',
-                sample=f'oracle port of the reference CPU path: 1 weight-search + 1 activation-search evaluation '
-                       f'(2x128 candidates) of blocks.0.attn.proj on 64 images ({secs:.1f} s), normalised to one '
-                       f'candidate on {args.images_per_gpu} images at the model-average GEMM cost')
+                sample=f'oracle port of the reference CPU path, stratified: ONE evaluation (128 candidates) of each of '
+                       f'the 21 sweep types of a {args.model} block on 8 images at the real layer sizes ({secs:.1f} s '
+                       f'in total), each type weighted by its count in a calibration and scaled linearly to '
+                       f'{args.images_per_gpu} images',
+                seconds_per_sweep_type_on_8_images={k: round(t_, 4) for k, t_ in per_type_s.items()})
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

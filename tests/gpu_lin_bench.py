@@ -65,11 +65,11 @@ def main():
         else:
             acs, acz = O.activation_candidates(x.view(128, 197, in_f), nl, 128, False)
             fn = lambda: sweep.linear_err_a(ctx, W3, b, wq, acs, acz, nl)
-        sweep.LIN_FUSED = True
+        os.environ['ADALOG_B200_LIN_FUSED'] = 'force'
         t_f = timeit(fn)
-        sweep.LIN_FUSED = False
+        os.environ['ADALOG_B200_LIN_FUSED'] = '0'
         t_p = timeit(fn)
-        sweep.LIN_FUSED = True
+        os.environ.pop('ADALOG_B200_LIN_FUSED')
         ops = 2.0 * 128 * tokens * in_f * out_f
         print(f'{which} {name:5s} K={in_f:5d} N={out_f:5d} {"log bf16" if log else "uniform i8"}: fused {t_f:7.3f} ms '
               f'({ops / t_f / 1e9:7.0f} Tops/s)   two-kernel {t_p:7.3f} ms ({ops / t_p / 1e9:7.0f} Tops/s)', flush=True)

@@ -29,15 +29,18 @@ def _setup(tokens, in_f, out_f, gelu=False, seed=3):
 
 
 def _both(fn):
-    from adalog_b200 import sweep
-    old = sweep.LIN_FUSED
+    import os
+    old = os.environ.get('ADALOG_B200_LIN_FUSED')
     try:
-        sweep.LIN_FUSED = True
+        os.environ['ADALOG_B200_LIN_FUSED'] = 'force'      # every shape that fits, not only the ones the heuristic picks
         fused = fn()
-        sweep.LIN_FUSED = False
+        os.environ['ADALOG_B200_LIN_FUSED'] = '0'
         plain = fn()
     finally:
-        sweep.LIN_FUSED = old
+        if old is None:
+            os.environ.pop('ADALOG_B200_LIN_FUSED', None)
+        else:
+            os.environ['ADALOG_B200_LIN_FUSED'] = old
     return fused, plain
 
 
@@ -79,7 +82,7 @@ def test_uniform_sweep_matches_two_kernel_path(tokens, in_f, out_f, bits):
         assert abs(fused[0, p].item() - ref.item()) <= 1e-5 * abs(ref.item()), (p, fused[0, p].item(), ref.item())
     # equal candidates give bit-equal scores (exact ties), wherever they sit
     perm = torch.randperm(128, device=DEV)
-    again = sweep.linear_err_a(ctx, W3, b, wq, acs[:, perm].contiguous(), acz[:, perm].contiguous(), nl)
+    again, _ = _both(lambda: sweep.linear_err_a(ctx, W3, b, wq, acs[:, perm].contiguous(), acz[:, perm].contiguous(), nl))
     assert torch.equal(again, fused[:, perm])
 
 
@@ -121,5 +124,5 @@ def test_log_sweep_matches_two_kernel_path(tokens, in_f, out_f, bits):
         assert torch.allclose(f.double(), p.double(), rtol=5e-6, atol=0), \
             ((f.double() - p.double()).abs() / p.double().abs()).max().item()
     perm = torch.randperm(128, device=DEV)
-    again = sweep.linear_err_log(ctx, W3, b, wq, lq, sc[:, perm].contiguous(), qc[:, perm].contiguous())
+    again, _ = _both(lambda: sweep.linear_err_log(ctx, W3, b, wq, lq, sc[:, perm].contiguous(), qc[:, perm].contiguous()))
     assert torch.equal(again, fused[:, perm])
