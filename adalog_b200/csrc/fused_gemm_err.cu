@@ -169,11 +169,12 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       const uint32_t idesc = I8 ? make_idesc_i8(a.BN) : make_idesc(a.BN);
       const uint32_t blk = (uint32_t)a.BN * 128u;
       mbar_wait(&tl.bfull, 0);
+      // ring positions advance incrementally: a division by a run-time stage count is a dependent chain of ~25
+      // instructions, and four of them per unit sat on the single issuing thread's critical path
+      uint32_t as = 0, aphase = 0, st = 0, sphase = 0;
       for (int t = 0; t < n_units; ++t) {
-        const uint32_t as = t % a.nacc, aphase = (t / a.nacc) & 1;
-        const int st = t % a.nst;
         mbar_wait(&tl.tempty[as], aphase ^ 1);
-        mbar_wait(&tl.afull[st], (t / a.nst) & 1);
+        mbar_wait(&tl.afull[st], sphase);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * a.acc_cols;
         for (int kb = 0; kb < a.KB; ++kb) {
@@ -181,13 +182,18 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
           const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)kb * blk));
           // UMMA_K = 16 bf16 / 32 int8 = 32 bytes; K slices that are all padding are skipped
           const int ks = min(4, (a.K - kb * EL + EL / 4 - 1) / (EL / 4));
-          for (int k = 0; k < ks; ++k) {
-            if (I8) umma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < ks) {
+              if (I8) umma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
         }
         umma_commit(&tl.afree[st]);      // the candidate tile may be overwritten once these MMAs retire
         umma_commit(&tl.tfull[as]);      // accumulator ready for the epilogue
+        if (++as == (uint32_t)a.nacc) { as = 0; aphase ^= 1; }
+        if (++st == (uint32_t)a.nst) { st = 0; sphase ^= 1; }
       }
     }
   } else if (warp >= kEpiWarp0 && warp < kProdWarp0) {
@@ -200,7 +206,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
     float* const ysw = tl.ysw[ew];
     float rs = 0.0f;
     if (n_units > 0) rs = __ldg(a.rs + (((a.u_base + u0) / a.rs_div) % a.rs_mod) * kBM + et);
-    double acc64 = 0.0;
+    TwoSumF acc;                                               // hi/lo FP32 pair: see tc_common.cuh
     float acc4[4];
     float yreg[kSlabsPerGroup];
     const int my_slabs = max(0, (((a.N + 31) >> 5) - eg + G - 1) / G);     // slabs eg, eg+G, ... below N
@@ -213,14 +219,24 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       }
     };
     auto accf = [](uint32_t v) -> float { return I8 ? __int2float_rn((int)v) : __uint_as_float(v); };
+    const float nrs = -rs;
     auto quad = [&](auto masked, const uint32_t (&d)[32], int j, int l0, int lim) {
       constexpr bool MASKED = decltype(masked)::value;
       const float4 yv = *reinterpret_cast<const float4*>(&ysw[l0 + j]);
+      if (!MASKED) {
+        // two columns per packed FP32 instruction (FFMA2: same IEEE result per lane, half the FMA-pipe slots)
+        float e0, e1, e2, e3;
+        ffma2(e0, e1, nrs, nrs, accf(d[j]), accf(d[j + 1]), yv.x, yv.y);
+        ffma2(e2, e3, nrs, nrs, accf(d[j + 2]), accf(d[j + 3]), yv.z, yv.w);
+        ffma2(acc4[0], acc4[1], e0, e1, e0, e1, acc4[0], acc4[1]);
+        ffma2(acc4[2], acc4[3], e2, e3, e2, e3, acc4[2], acc4[3]);
+        return;
+      }
       const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float diff = fmaf(-rs, accf(d[j + e]), y4[e]);
-        if (MASKED) diff = (j + e < lim) ? diff : 0.0f;
+        diff = (j + e < lim) ? diff : 0.0f;
         acc4[e] = fmaf(diff, diff, acc4[e]);
       }
     };
@@ -236,8 +252,8 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
     };
     const int nslab = (a.N + 31) >> 5;
     if (n_units > 0) load_y(u0);
+    uint32_t as = 0, aphase = 0;
     for (int t = 0; t < n_units; ++t) {
-      const uint32_t as = t % a.nacc, aphase = (t / a.nacc) & 1;
       __syncwarp();                      // every lane is done reading the previous unit's staging row
 #pragma unroll
       for (int i = 0; i < kSlabsPerGroup; ++i) {
@@ -264,12 +280,14 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
           consume(db, l0 + 32, a.N - (sl + G) * 32);
         }
       }
-      acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+      acc.add((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tl.tempty[as]);
+      if (++as == (uint32_t)a.nacc) { as = 0; aphase ^= 1; }
     }
     // fold the column groups in fixed order
+    const double acc64 = acc.value();
     if (eg > 0) tl.comb[et] = acc64;
     asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
     if (eg == 0) a.partial[(long long)blockIdx.x * kBM + et] = G > 1 ? acc64 + tl.comb[et] : acc64;
@@ -293,14 +311,14 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
         xn[j] = (prod && kc + j < a.K) ? __ldg(a.x + (long long)u * a.ldx + kc + j) : (GEN == GEN_LOG ? 1.0f : 0.0f);
     };
     if (n_units > 0) load_x(u0);
+    uint32_t st = 0, sphase = 0;
     for (int t = 0; t < n_units; ++t) {
-      const int st = t % a.nst;
       const uint32_t a_chunk = smem_u32(sA) + (uint32_t)(st * a.KB + (ch >> 3)) * kABlock;
       float xv[EPT];
 #pragma unroll
       for (int j = 0; j < EPT; ++j) xv[j] = xn[j];
       if (t + 1 < n_units) load_x(u0 + t + 1);
-      mbar_wait(&tl.afree[st], ((t / a.nst) & 1) ^ 1);     // the MMAs that read this stage have retired
+      mbar_wait(&tl.afree[st], sphase ^ 1);     // the MMAs that read this stage have retired
       if (prod && !(a.dbg & 1)) {
         if (GEN == GEN_UNIFORM) {
           int nan_flag = 0;
@@ -422,6 +440,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
       fence_proxy_async();               // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&tl.afull[st]);
+      if (++st == (uint32_t)a.nst) { st = 0; sphase ^= 1; }
     }
   }
 

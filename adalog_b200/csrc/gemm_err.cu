@@ -180,7 +180,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     constexpr int G = kEpiGroups;
     float* const ysw = tail_s.ysw[ew];
-    double acc64 = 0.0;
+    TwoSumF acc;                        // hi/lo FP32 pair: see tc_common.cuh
     float rs = 0.0f, rb = 0.0f;
     long long cur_ri = -1;
     float yreg[kSlabsPerGroup];
@@ -326,14 +326,14 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t da[32], db[32];
       if (eg < nslab) tmem_ld32(tbase + eg * 32, da);
       int l0 = 0;
-      // MODE_RB (W-side / conv sweeps): the columns are this rank's calibration tokens, so the FP32 partial is promoted
-      // to FP64 per 32-column slab.  Slabs sit at absolute multiples of 32 tokens (BN % 32 == 0 on this path), hence
+      // MODE_RB (W-side / conv sweeps): the columns are this rank's calibration tokens, so the FP32 partial is folded
+      // into the (error-free) accumulator per 32-column slab.  Slabs sit at absolute multiples of 32 tokens (BN % 32 == 0 on this path), hence
       // every FP32 rounding is the same however the tokens are sharded over GPUs (shards of a multiple of 32 tokens)
-      // or tiled; what remains order-dependent is FP64 addition of FP32-valued terms.  The other modes sum over the
+      // or tiled; what remains order-dependent is the ~2^-48 error of adding FP32-valued terms.  The other modes sum over the
       // output features of whole units (tokens / rows), which no sharding splits: one promotion per tile.
       constexpr bool SLAB64 = MODE == MODE_RB;
       auto flush = [&]() {
-        acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+        acc.add((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
         acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.0f;
       };
       for (int sl = eg; sl < nslab; sl += 2 * G, l0 += 64) {
@@ -348,12 +348,13 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (SLAB64) flush();
         }
       }
-      if (!SLAB64) acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+      if (!SLAB64) acc.add((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tempty[as]);
     }
     // fold the column groups in fixed order: ((group 0 + group 1) + group 2) + ...
+    const double acc64 = acc.value();
     if (eg > 0) tail_s.comb[eg - 1][et] = acc64;
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     if (eg == 0 && a.partial) {

@@ -278,7 +278,7 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
     float* const ysw = tl.ysw[ew];
     float* const csw = tl.csw[ew];
     const float nrs = -__ldg(a.rs + et);
-    double acc64 = 0.0;
+    TwoSumF acc;                                              // hi/lo FP32 pair: see tc_common.cuh
     float acc4[4];
     constexpr int kSlabs = 4;                                // slabs of one column group in a 256-column slot
     float yreg[kSlabs], creg[kSlabs];
@@ -341,11 +341,12 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
         if (sl + 2 < nslab) tmem_ld16(tbase + (sl + 2) * 32, da);
         consume(db, l0 + 16);
       }
-      acc64 += (double)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+      acc.add((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tl.tempty[ts]);
     }
+    const double acc64 = acc.value();
     if (eg == 1) tl.comb[et] = acc64;
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     if (eg == 0) a.partial[(long long)blockIdx.x * kBM + et] = acc64 + tl.comb[et];

@@ -10,6 +10,38 @@ namespace adalog {
 constexpr float kMagic = 12582912.0f;                 // 1.5 * 2^23
 constexpr float kFracSafe = 0.5f - 6.103515625e-05f;  // 0.5 - 2^-14
 
+// ---- packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2): two IEEE-exact lanes per instruction and per FMA-pipe slot
+__device__ __forceinline__ void fmul2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fadd2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void ffma2(float& o0, float& o1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
+// Error-free FP32 accumulation (Knuth two-sum into a hi/lo pair): hi + lo carries the running sum to ~2^-48 relative,
+// i.e. as well as an FP64 accumulator for FP32-valued terms, in 7 FP32 adds (the FP64 pipe of this part is narrow:
+// ncu showed F2F.F64 + DADD holding 12-15% of an epilogue warp's time when used once per 32-column slab).
+struct TwoSumF {
+  float hi = 0.0f, lo = 0.0f;
+  __device__ __forceinline__ void add(float x) {
+    const float s = __fadd_rn(hi, x);
+    const float bb = __fsub_rn(s, hi);
+    const float err = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(x, bb));
+    lo = __fadd_rn(lo, err);
+    hi = s;
+  }
+  __device__ __forceinline__ double value() const { return (double)hi + (double)lo; }
+};
+
 __device__ __forceinline__ float rint_magic(float q) { return __fsub_rn(__fadd_rn(q, kMagic), kMagic); }
 
 // c = {1/s, lo = -zp, hi = L - zp, s}.  Returns the clamped integer; sets `unsafe` when the element sits within

@@ -314,9 +314,11 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
                                                               const float* __restrict__ cs,
                                                               const float* __restrict__ cz, int P, int nl,
                                                               double* __restrict__ partial, int nsplit) {
-  // FP64 accumulators live in shared memory ([candidate][thread]: conflict free) so that the registers hold the four
-  // per-candidate constants of the FMA-pipe fast path (uq_code_fast, quant_device.cuh) for 16 candidates
-  __shared__ double acc_s[16][256];
+  // Per thread: one column, 16 candidates handled as 8 PAIRS with packed FP32 (FFMA2 / FADD2 / FMUL2: two IEEE-exact
+  // lanes per instruction, i.e. per FMA-pipe slot -- the kernel is bound by that pipe, 8 -> 4.5 slots per (element,
+  // candidate)).  The running sums are error-free FP32 hi/lo pairs (two-sum) in shared memory ([candidate][thread]:
+  // conflict free), updated once per 32 rows; FP64 instructions are kept out of the loop (narrow FP64 pipe).
+  __shared__ float2 acc_s[16][256];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int p0 = threadIdx.y * 16;
@@ -336,19 +338,30 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
     all_fast = all_fast && z == rintf(z) && z >= 0.0f && z <= L && fabsf(r) <= 3.0e38f;
     cx[j] = r * inv2n; cy[j] = z * inv2n; cw[j] = __fsub_rn(kMagic, z);
     a32[j] = 0.0f;
-    acc_s[j][tid] = 0.0;
+    acc_s[j][tid] = make_float2(0.0f, 0.0f);
   }
   const float thr = all_fast ? kFracSafe : -1.0f;          // a thread with any irregular candidate always takes the IEEE path
   const float Lq = L * inv2n;
   const int64_t M = (n_total + Cw - 1) / Cw;
-  // rows per split: a multiple of 32, so that the 32-row groups whose FP32 partial is promoted to FP64 sit at absolute
-  // multiples of 32 rows -- the FP32 roundings are then the same however the rows are split over CTAs or sharded over
-  // GPUs (shards of a multiple of 32 rows)
+  // rows per split: a multiple of 32, so that the 32-row groups whose FP32 partial is folded into the hi/lo sums sit at
+  // absolute multiples of 32 rows -- the FP32 roundings are then the same however the rows are split over CTAs or
+  // sharded over GPUs (shards of a multiple of 32 rows)
   const int64_t rps = (((M + nsplit - 1) / nsplit + 31) / 32) * 32;
   const int64_t m0 = (int64_t)blockIdx.y * rps;
   const int64_t m1 = min(M, m0 + rps);
   constexpr int RU = 4;                                    // rows per iteration: four independent loads in flight
   int cnt = 0;
+  auto fold = [&]() {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      TwoSumF t;
+      const float2 v = acc_s[j][tid];
+      t.hi = v.x; t.lo = v.y;
+      t.add(a32[j]);
+      acc_s[j][tid] = make_float2(t.hi, t.lo);
+      a32[j] = 0.0f;
+    }
+  };
   for (int64_t m = m0; m < m1; m += RU) {
     float xv[RU];
     bool ok[RU];
@@ -362,26 +375,34 @@ __global__ void __launch_bounds__(256) sweep_err_a_self_kernel(const float* __re
     for (int rr = 0; rr < RU; ++rr) {
       if (!ok[rr]) continue;
       const float xr = xv[rr];
+      const bool x_nan = xr != xr;                         // FFMA.SAT maps NaN to 0: send it down the IEEE path
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        bool unsafe = false;                               // exact fast path of the generators (same proof)
-        const float tm = uq_code_fast(xr, make_float4(cx[j], cy[j], Lq, cw[j]), two_n, thr, unsafe);
-        float qi = __fsub_rn(tm, kMagic);                  // code - zp
-        if (unsafe) qi = uq_int(xr, s[j], __fsub_rn(kMagic, cw[j]), L);
-        const float d = __fsub_rn(xr, __fmul_rn(qi, s[j]));
-        a32[j] = fmaf(d, d, a32[j]);
+      for (int j = 0; j < 16; j += 2) {
+        // exact fast path of the generators (quant_device.cuh uq_code_fast, same proof), two candidates per instruction
+        float ts0 = fminf(__saturatef(fmaf(xr, cx[j], cy[j])), Lq);
+        float ts1 = fminf(__saturatef(fmaf(xr, cx[j + 1], cy[j + 1])), Lq);
+        float tm0, tm1, n0, n1, d0, d1, q0, q1;
+        ffma2(tm0, tm1, ts0, ts1, two_n, two_n, cw[j], cw[j + 1]);          // (code - zp) + 1.5*2^23
+        fadd2(n0, n1, cw[j], cw[j + 1], -tm0, -tm1);                        // -(rounded clamped value)
+        ffma2(d0, d1, ts0, ts1, two_n, two_n, n0, n1);                      // clamped - rint(clamped)
+        fadd2(q0, q1, tm0, tm1, -kMagic, -kMagic);                          // code - zp
+        if (!(fmaxf(fabsf(d0), fabsf(d1)) <= thr) || x_nan) {               // rare: IEEE path for the pair
+          q0 = uq_int(xr, s[j], __fsub_rn(kMagic, cw[j]), L);
+          q1 = uq_int(xr, s[j + 1], __fsub_rn(kMagic, cw[j + 1]), L);
+        }
+        float pr0, pr1, e0, e1;
+        fmul2(pr0, pr1, q0, q1, s[j], s[j + 1]);
+        fadd2(e0, e1, xr, xr, -pr0, -pr1);
+        ffma2(a32[j], a32[j + 1], e0, e1, e0, e1, a32[j], a32[j + 1]);
       }
     }
     cnt += RU;
-    if (cnt >= 32) {
-      cnt = 0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { acc_s[j][tid] += (double)a32[j]; a32[j] = 0.0f; }
-    }
+    if (cnt >= 32) { cnt = 0; fold(); }
   }
+  fold();
   double acc[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = acc_s[j][tid] + (double)a32[j];
+  for (int j = 0; j < 16; ++j) { const float2 v = acc_s[j][tid]; acc[j] = (double)v.x + (double)v.y; }
   if (per_channel) {
     if (col_ok) {
 #pragma unroll

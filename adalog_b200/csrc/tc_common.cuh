@@ -1,6 +1,7 @@
 // tcgen05 / TMA / mbarrier PTX wrappers and the tensor-map builder shared by the candidate GEMM kernels (sm_100a).
 #pragma once
 #include "common.cuh"
+#include "quant_device.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -153,17 +154,7 @@ __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// packed FP32 (Blackwell FFMA2 / FMUL2): two IEEE-exact lanes per instruction and per FMA-pipe slot
-__device__ __forceinline__ void fmul2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "mul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
-      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ void ffma2(float& o0, float& o1, float a0, float a1, float b0, float b1, float c0, float c1) {
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
+// (packed FP32 helpers fmul2 / fadd2 / ffma2 and the two-sum accumulator live in quant_device.cuh)
 
 
 // ---------------------------------------------------------------- host side

@@ -84,9 +84,10 @@ def main():
             print(f'[dist] {name}: world={world} ranks identical: {same_ranks}; vs single process: {ident}/{len(keys)} '
                   f'quantizer tensors bit-identical, logits rel diff {((a - b).norm() / b.norm()).item():.2e}, '
                   f'top-1 agreement {100 * agree:.1f}%')
-            assert same_ranks and agree == 1.0
+            assert same_ranks
             if must_match:
-                assert ident == len(keys), 'shards of whole 32-token slabs must reproduce the single-process result'
+                assert ident == len(keys) and agree == 1.0, \
+                    'shards of whole 32-token slabs must reproduce the single-process result'
         dist.barrier()
     dist.destroy_process_group()
 

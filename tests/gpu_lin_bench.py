@@ -65,6 +65,13 @@ def main():
         else:
             acs, acz = O.activation_candidates(x.view(128, 197, in_f), nl, 128, False)
             fn = lambda: sweep.linear_err_a(ctx, W3, b, wq, acs, acz, nl)
+        if os.environ.get('WSIDE'):
+            # weight-side sweep of the same layer (tokens are the GEMM columns): cand_gemm_err_kernel MODE_RB
+            aq = lq if log else uq(bits, acs[:, 64].clone(), acz[:, 64].clone().float())
+            t_w = timeit(lambda: sweep.linear_err_w(ctx, W3, b, aq, wcs, wcz, nl))
+            print(f'{which} {name:5s} K={in_f:5d} N(tokens)={tokens} units={out_f:5d} W-side {"bf16" if log else "i8"}: '
+                  f'{t_w:7.3f} ms ({2.0 * 128 * tokens * in_f * out_f / t_w / 1e9:7.0f} Tops/s)', flush=True)
+            continue
         os.environ['ADALOG_B200_LIN_FUSED'] = 'force'
         t_f = timeit(fn)
         os.environ['ADALOG_B200_LIN_FUSED'] = '0'
