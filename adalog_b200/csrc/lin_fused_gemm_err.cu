@@ -411,16 +411,19 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
             // compiles to EPT serially dependent FSETPs); d is finite: ts is saturated to [0, 1]
             float dm[EPT];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-              float ts = __saturatef(fmaf(xv[j], c.x, c.y));
-              ts = fminf(ts, c.z);
-              tm[j] = fmaf(ts, ncode_f, c.w);
-              dm[j] = fabsf(fmaf(ts, ncode_f, -__fsub_rn(tm[j], c.w)));
+            for (int j = 0; j < EPT; j += 2) {
+              // uq_code_fast (quant_device.cuh) on two elements per packed FP32 instruction
+              const float ts0 = fminf(__saturatef(fmaf(xv[j], c.x, c.y)), c.z);
+              const float ts1 = fminf(__saturatef(fmaf(xv[j + 1], c.x, c.y)), c.z);
+              float n0, n1;
+              ffma2(tm[j], tm[j + 1], ts0, ts1, ncode_f, ncode_f, c.w, c.w);      // (code - zp) + 1.5*2^23
+              fadd2(n0, n1, c.w, c.w, -tm[j], -tm[j + 1]);                        // -(rounded clamped value)
+              ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);        // clamped - rint(clamped)
             }
 #pragma unroll
             for (int w2 = EPT / 2; w2 > 0; w2 >>= 1) {
 #pragma unroll
-              for (int j = 0; j < w2; ++j) dm[j] = fmaxf(dm[j], dm[j + w2]);
+              for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
             }
             if (!(dm[0] <= thr) || nan_flag != 0) {           // rare: redo the chunk on the IEEE path
               const float2 sz = tl.cand_sz[p];
@@ -452,13 +455,17 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
         } else {
           // post-GELU AdaLog search form (linear.py:872-878, :913-919): see gen_log_cand_lut_kernel (quant_kernels.cu)
           // for the derivation of the exact fast path; same arithmetic, same margins, same IEEE fallback.  xv = lx here.
-          float gm[EPT];
+          // element part of the rounding margin, 6e-7 |lx| + 2e-7 (quant_kernels.cu): the chunk's LARGEST is used for
+          // all of its elements -- conservative (a few more chunks take the IEEE path, still ~1e-4 of them), and the
+          // per-element check shrinks to |d| <= 0.5 - candidate margin - gmax * mul
+          float gmax = 0.0f;
           bool clamp_region = false;
 #pragma unroll
           for (int j = 0; j < EPT; ++j) {
-            gm[j] = 6e-7f * fabsf(xv[j]) + 2e-7f;
+            gmax = fmaxf(gmax, fabsf(xv[j]));
             clamp_region |= !(xv[j] <= lim_min);              // near the reference's 1e-15 clamp, x <= 0 or NaN
           }
+          gmax = 6e-7f * gmax + 2e-7f;
           int clamp_flag = clamp_region ? 1 : 0;
           asm volatile("" : "+r"(clamp_flag));
           auto l_gen = [&](int p) -> uint4 {
@@ -467,22 +474,26 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
             uint32_t row = lut_bias + (uint32_t)(p * lw) * 4u;
             asm volatile("" : "+r"(row));
             float dm[EPT], v[EPT];
+            const float lim_d = fmaf(-gmax, c.w, half);
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-              const float ts = __saturatef(fmaf(xv[j], c.x, c.y));
-              const float tm = fmaf(ts, ncode_f, kMagic);
-              const float d = fmaf(ts, ncode_f, -__fsub_rn(tm, kMagic));
-              dm[j] = fmaf(gm[j], c.w, fabsf(d));             // |d| + element margin, to be <= 0.5 - candidate margin
-              float val;
-              asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(__float_as_uint(tm) * 4u + row));
-              v[j] = val;
+            for (int j = 0; j < EPT; j += 2) {
+              const float ts0 = __saturatef(fmaf(xv[j], c.x, c.y));
+              const float ts1 = __saturatef(fmaf(xv[j + 1], c.x, c.y));
+              float tm0, tm1, n0, n1;
+              ffma2(tm0, tm1, ts0, ts1, ncode_f, ncode_f, kMagic, kMagic);
+              fadd2(n0, n1, kMagic, kMagic, -tm0, -tm1);
+              ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);
+              float val0, val1;
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val0) : "r"(__float_as_uint(tm0) * 4u + row));
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val1) : "r"(__float_as_uint(tm1) * 4u + row));
+              v[j] = val0; v[j + 1] = val1;
             }
 #pragma unroll
             for (int w2 = EPT / 2; w2 > 0; w2 >>= 1) {
 #pragma unroll
-              for (int j = 0; j < w2; ++j) dm[j] = fmaxf(dm[j], dm[j + w2]);
+              for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
             }
-            if (!(dm[0] <= half) || clamp_flag != 0) {
+            if (!(dm[0] <= lim_d) || clamp_flag != 0) {
               const float2 qs = tl.cand_sz[p];
               return log_chunk_slow(a.x + (long long)u * a.ldx + kc, min(EPT, a.K - kc), sh, a.shift != nullptr, qs.y, qs.x,
                                     tl.mt, ncode_f);
