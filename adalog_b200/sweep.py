@@ -538,7 +538,7 @@ def _use_fused(K, N, i8, log, n_levels):
     a long reduction (P.V value sweep, K = 197) its 14 worker warps are short of issue slots (2.3 vs 1.9 ms)."""
     if not FUSED or ops.fused_plan(K, N, i8, log, n_levels) is None:
         return False
-    return log or K <= 128
+    return log or K <= 128 or os.environ.get('ADALOG_B200_FUSED_LONGK', '0') == '1'
 
 
 def _run_fused(x2d, K, Bm, N, U, UG, y, ldy, rs, H, n_levels, P, i8=False, **cand):
