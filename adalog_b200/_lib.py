@@ -75,6 +75,10 @@ SIGNATURES = {
     'adalog_gen_log_cand': [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp],
     'adalog_gen_log_fixed': [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp],
     'adalog_gen_split3': [c_vp, c_i64, c_int, c_i64, c_vp, c_int, c_vp],
+    'adalog_select_init': [c_vp, c_i64, c_int, c_vp, c_vp],
+    'adalog_select_hist': [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp],
+    'adalog_select_scan': [c_vp, c_i64, c_int, c_int, c_vp],
+    'adalog_select_finish': [c_vp, c_i64, c_int, c_vp, c_vp],
     'adalog_cand_gemm_err_grid': [ctypes.POINTER(GemmErrArgs)],
     'adalog_cand_gemm_err': [ctypes.POINTER(GemmErrArgs), c_vp],
     'adalog_fused_cand_gemm_err_grid': [ctypes.POINTER(FusedArgs)],
@@ -84,6 +88,9 @@ SIGNATURES = {
     'adalog_gemm_dequant': [ctypes.POINTER(GemmErrArgs), c_vp, c_i64, c_i64, c_vp],
     'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
 }
+
+# exported functions that do not return an int status (bound separately in load())
+OTHER_SYMBOLS = {'adalog_last_error', 'adalog_select_workspace_bytes', 'adalog_select_hist_ptr'}
 
 _lib = None
 # kernels launched through this binding (bench.py reports it as gpu_launches)
@@ -111,6 +118,10 @@ def load():
         fn.restype = ctypes.c_int
     lib.adalog_last_error.argtypes = []
     lib.adalog_last_error.restype = ctypes.c_char_p
+    lib.adalog_select_workspace_bytes.argtypes = [c_i64, c_int]
+    lib.adalog_select_workspace_bytes.restype = ctypes.c_int64
+    lib.adalog_select_hist_ptr.argtypes = [c_vp, c_i64, c_int]
+    lib.adalog_select_hist_ptr.restype = ctypes.c_void_p
     _lib = lib
     return lib
 

@@ -212,6 +212,42 @@ def sweep_err_a_self(x, cs, cz, n_levels, per_channel):
     return partial.sum(dim=0)
 
 
+# ------------------------------------------------------------------------------------------ order statistics
+def select_kth(x2d, ranks, positive_only=False, reduce_hist=None, rows_total=None, row0=0):
+    """Exact order statistics by radix selection (adalog_select_*): x2d [rows, n] FP32 with contiguous rows, ranks [T]
+    int64 on the device (T <= 8, the same for every row) -> [rows_total, T] float32 = sort(row)[ranks], bit for bit.
+    reduce_hist: callable(hist_tensor) -> hist_tensor, e.g. an all-reduce(SUM) over the ranks of a data-parallel job
+    (each holding a shard of every row, or local rows [row0, row0 + rows) of rows_total): the statistics are then those
+    of the union of the shards."""
+    _cuda(x2d, ranks)
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1
+    rows, n = x2d.shape
+    R = int(rows_total if rows_total is not None else rows)
+    T = int(ranks.numel())
+    lib = _lib.load()
+    nbytes = lib.adalog_select_workspace_bytes(R, T)
+    if nbytes < 0:
+        raise AdalogError('select_kth: at most 8 target ranks per call')
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x2d.device)
+    rk = ranks.to(torch.int64).contiguous()
+    call('adalog_select_init', _p(ws), R, T, _p(rk), _stream())
+    hist = None
+    if reduce_hist is not None:
+        off = R * T * 16
+        hist = ws[off:off + R * T * 256 * 4].view(torch.int32)
+    for p in range(4):
+        call('adalog_select_hist', _p(x2d), rows, n, int(x2d.stride(0)), _p(ws), R, int(row0), T, p,
+             int(bool(positive_only)), _stream())
+        if reduce_hist is not None:
+            red = reduce_hist(hist)
+            if red.data_ptr() != hist.data_ptr():
+                hist.copy_(red)
+        call('adalog_select_scan', _p(ws), R, T, p, _stream())
+    out = torch.empty(R, T, dtype=torch.float32, device=x2d.device)
+    call('adalog_select_finish', _p(ws), R, T, _p(out), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------ generators
 def _rows2d(x):
     if x.dim() != 2 or x.stride(1) != 1:

@@ -11,6 +11,9 @@ from .. import _const
 from ..utils import dist as adist
 
 
+SELECT_MIN_N = 1 << 16      # rows at least this long are selected by radix passes instead of sorted
+
+
 def candidate_chunks(P, tile=128):
     """slices of at most `tile` candidates (the kernels score one TMEM-lane tile of 128 per pass)"""
     return [(p0, min(P, p0 + tile)) for p0 in range(0, P, tile)]
@@ -110,20 +113,33 @@ def quantile_pair(x, pct, dim, local=False, seg=None):
     n = pct.numel()
     q = (_const.pct_pair(float(pct[0]), float(pct[1]), x.device) if (n == 2 and not pct.is_cuda)
          else torch.cat([pct, 1 - pct]).to(x.device))
-    if local or not adist.active():
+    dist_on = adist.active() and not local
+    # Exact radix selection (csrc/select_kernels.cu) instead of a full sort wherever the reduced dimension is long:
+    # four passes over the data, and under data parallelism four all-reduces of the digit histograms instead of
+    # sort + bisection.  Short rows (weights, per-channel statistics) stay on torch.quantile.
+    xs = x.movedim(dim, -1)
+    use_select = (x.is_cuda and x.dtype == torch.float32 and xs.shape[-1] >= SELECT_MIN_N and q.numel() * 2 <= 8
+                  and seg is None)
+    if not dist_on and not use_select:
         both = torch.quantile(x, q, dim=dim)
         return both[:n], both[n:]
-    xs = x.movedim(dim, -1)
     lead = xs.shape[:-1]
-    srt, _ = xs.reshape(-1, xs.shape[-1]).contiguous().sort(dim=-1)
-    ranks_per_seg = adist.world_size() // (seg[1] if seg is not None else 1)
-    n_glob = srt.shape[1] * ranks_per_seg
-    ranks = q.to(srt.dtype) * (n_glob - 1)                   # torch.quantile: q * last_index in the input dtype
+    rows2d = xs.reshape(-1, xs.shape[-1]).contiguous()
+    ranks_per_seg = (adist.world_size() // (seg[1] if seg is not None else 1)) if dist_on else 1
+    n_glob = rows2d.shape[1] * ranks_per_seg
+    ranks = q.to(rows2d.dtype) * (n_glob - 1)                # torch.quantile: q * last_index in the input dtype
     below = ranks.to(torch.int64)
     weights = ranks - below
     above = ranks.ceil().to(torch.int64)
-    vals = adist.kth_values(srt, torch.cat([below, above]), seg)       # [rows, 2nq] or [n_seg, rows, 2nq]
     nq = q.numel()
+    if use_select:
+        from .. import ops
+        vals = ops.select_kth(rows2d, torch.cat([below, above]), reduce_hist=adist.all_reduce_sum if dist_on else None)
+        vals = vals.t()                                                 # [2nq, rows]
+        res = vals[:nq].clone().lerp_(vals[nq:], weights.view(-1, 1)).reshape(nq, *lead)
+        return res[:n], res[n:]
+    srt, _ = rows2d.sort(dim=-1)
+    vals = adist.kth_values(srt, torch.cat([below, above]), seg)       # [rows, 2nq] or [n_seg, rows, 2nq]
     if seg is not None:
         vals = vals.permute(2, 1, 0)                                    # [2nq, rows, n_seg]
         res = vals[:nq].clone().lerp_(vals[nq:], weights.view(-1, 1, 1))

@@ -478,15 +478,30 @@ class PostGeluLogBasedBatchingQuantLinear(AsymmetricallyBatchingQuantLinear):
         vals = adist.kth_values(srt.view(1, -1), ranks.view(-1)).view(-1)
         return torch.where(torch.isinf(vals) | (counts <= 0), torch.zeros_like(vals), vals)
 
+    @staticmethod
+    def _positive_percentile_select(x_local, q):
+        """positive_percentile (of the concatenation of all ranks' shards under data parallelism) by exact radix
+        selection instead of a full sort (csrc/select_kernels.cu): count the positive entries, then the element of rank
+        ceil(count*q)-1 among them; entries <= 0 are keyed as +inf inside the kernel."""
+        from .. import ops
+        counts = adist.all_reduce_sum((x_local > 0).sum().to(torch.int64).view(1)).float()
+        ranks = ((counts * q).ceil().long() - 1).clamp(min=0)
+        vals = ops.select_kth(x_local.view(1, -1), ranks.view(-1), positive_only=True,
+                              reduce_hist=adist.all_reduce_sum if adist.active() else None).view(-1)
+        return torch.where(torch.isinf(vals) | (counts <= 0), torch.zeros_like(vals), vals)
+
     def calculate_percentile_activation_candidates(self, l=0.9, r=1.0):
         """reference linear.py:800-814"""
-        # the calibration input does not change between search rounds: one sort per module
+        # the calibration input does not change between search rounds: one selection per module
         cache = self._ctx.__dict__.setdefault('_pct_cache', {})
         if ('pos', l, r) not in cache:
             x = self._ctx.x2d.reshape(-1)
             q = _const.floats((l, r), x.device)
-            cache[('pos', l, r)] = (self._positive_percentile_dist(x, q) if adist.active()
-                                    else self.positive_percentile(x, q))
+            if x.is_cuda and x.numel() >= _fpcs.SELECT_MIN_N:
+                cache[('pos', l, r)] = self._positive_percentile_select(x, q)
+            else:
+                cache[('pos', l, r)] = (self._positive_percentile_dist(x, q) if adist.active()
+                                        else self.positive_percentile(x, q))
         cand = cache[('pos', l, r)] + self.a_quantizer.shift.item()
         cand = cand.unsqueeze(0)
         ramp = _const.ramp(self.eq_n, cand.device).view(1, -1)

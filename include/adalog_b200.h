@@ -108,6 +108,26 @@ int adalog_gen_log_fixed(const float* x, int64_t R, int K, int64_t ldx, const fl
  * that a krep=3 candidate operand reproduces the FP32 product to 2^-24. */
 int adalog_gen_split3(const float* x, int64_t R, int K, int64_t ldx, uint16_t* out, int kpad, void* stream);
 
+/* ---------------------------------------------------------------- exact order statistics by radix selection (K11)
+ * replaces: the full sorts behind torch.quantile / Tensor.sort of the candidate seeding -- linear.py:432-481
+ * (calculate_percentile_*_candidates), :763-814 (positive_percentile), matmul.py:211-240.
+ *
+ * x: `rows` rows of n contiguous FP32 elements (row r at x + r*row_stride); ranks[T] (T <= 8, 0-based, the same for
+ * every row); out[rows*T] = the ranks[t]-th smallest element of each row, bit for bit what sort(row)[ranks[t]] holds
+ * (NaN last; a selected zero comes back as +0.0).  positive_only: elements <= 0 count as +inf (linear.py:763-798).
+ * Four passes of 8 bits: adalog_select_hist(pass) accumulates the histogram of the next digit, adalog_select_scan(pass)
+ * descends.  A data-parallel caller whose ranks each hold local_rows of the `rows` (row0 = its offset; or the same rows,
+ * sharded along n, with row0 = 0) all-reduces (SUM) the uint32 histograms at adalog_select_hist_ptr between the two
+ * calls: every rank then selects from the union of the shards.  The workspace (adalog_select_workspace_bytes) is
+ * caller-owned; nothing is allocated inside. */
+int64_t adalog_select_workspace_bytes(int64_t rows, int T);
+void* adalog_select_hist_ptr(void* workspace, int64_t rows, int T);
+int adalog_select_init(void* workspace, int64_t rows, int T, const long long* ranks, void* stream);
+int adalog_select_hist(const float* x, int64_t local_rows, int64_t n, int64_t row_stride, void* workspace, int64_t rows,
+                       int64_t row0, int T, int pass, int positive_only, void* stream);
+int adalog_select_scan(void* workspace, int64_t rows, int T, int pass, void* stream);
+int adalog_select_finish(const void* workspace, int64_t rows, int T, float* out, void* stream);
+
 /* ---------------------------------------------------------------- candidate-batched GEMM + fused error (K5-K10)
  * replaces: the F.linear / @ / F.conv2d + _get_similarity + mean/sum chains of linear.py:355-384, :394-423,
  * :856-890, :898-931, matmul.py:135-163, :173-201, :321-351, conv.py:226-256.

@@ -25,7 +25,7 @@ def test_library_exports_header_symbols():
 
 def test_binding_covers_header():
     syms = set(declared_symbols())
-    bound = set(_lib.SIGNATURES) | {'adalog_last_error'}
+    bound = set(_lib.SIGNATURES) | set(_lib.OTHER_SYMBOLS)
     assert syms == bound, (syms - bound, bound - syms)
     lib = _lib.load()
     assert lib.adalog_version() >= 100
