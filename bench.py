@@ -418,6 +418,29 @@ def run_ours(args):
         return args.images_per_gpu / (e0.elapsed_time(e1) / 1e3), torch.cat(logits)
 
     fq_img_s, logits_ref = fq_rate(32)
+    # checker: the same calibrated model with every quantizer forward evaluated by the oracle's torch ops on this GPU
+    # (the reference's own forward composition): the default forward must reproduce it bit for bit
+    fwd_parity = None
+    if rank == 0 and not args.no_parity:
+        for pth in (os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+            if pth not in sys.path:
+                sys.path.insert(0, pth)
+        import _oracle_backend as fake
+        from gpu_parity import _Patch
+        mp = _Patch()
+        try:
+            from adalog_b200 import ops as _ops
+            for name in ('uniform_fakequant', 'log_fakequant', 'twin_fakequant'):
+                mp.setattr(_ops, name, getattr(fake, name))
+            with torch.no_grad():
+                ref_fwd = torch.cat([model(dev_images[i:i + 32]) for i in range(0, args.images_per_gpu, 32)])
+        finally:
+            mp.undo()
+        fwd_parity = dict(default_forward_bit_identical_to_reference_forward=bool(torch.equal(ref_fwd, logits_ref)),
+                          top1_agreement=float((ref_fwd.argmax(-1) == logits_ref.argmax(-1)).float().mean()),
+                          max_abs_logit_diff=float((ref_fwd - logits_ref).abs().max()), images=int(ref_fwd.shape[0]),
+                          what='calibrated model, default forward (sm_100a fake-quant kernels + FP32 products) vs the '
+                               'same model with the quantizer forwards evaluated by the oracle\'s torch ops on this GPU')
     # the same default forward replayed from a CUDA graph (batch 32 is launch-latency bound)
     graphed_img_s, graphed_equal = None, None
     try:
@@ -441,7 +464,7 @@ def run_ours(args):
     fq_tc, logits_tc = fq_rate(32)
     fq_tc_big, _ = fq_rate(args.images_per_gpu)
     set_tensor_core_forward(model, False)
-    fq_extra = dict(batch32_img_per_s=fq_img_s, batch32_cuda_graph_img_per_s=graphed_img_s,
+    fq_extra = dict(parity=fwd_parity, batch32_img_per_s=fq_img_s, batch32_cuda_graph_img_per_s=graphed_img_s,
                     batch32_cuda_graph_bit_identical=graphed_equal, full_batch_img_per_s=fq_big, tensor_core_batch32_img_per_s=fq_tc,
                     tensor_core_full_batch_img_per_s=fq_tc_big,
                     tensor_core_top1_agreement=float((logits_tc.argmax(-1) == logits_ref.argmax(-1)).float().mean()),

@@ -83,6 +83,23 @@ ms = timed(lambda: O.uniform_fakequant(x, s1, z1, 8), 3)
 res['reference eager uniform chain (torch)'] = 8 * n / ms / 1e6
 ms = timed(lambda: O.adalog_fakequant(p, one.view(1, 1, 1, 1), q, 8, t1, t2), 3)
 res['reference eager adalog chain (torch)'] = 8 * p.numel() / ms / 1e6
+# self-error sweep of the activations (linear.py:320-345): 4 B per element read ONCE for all 128 candidates -- by bytes it
+# is far from the HBM roof because 128 candidates x ~7 FP32 operations are evaluated per element (FMA-pipe bound)
+xa = torch.randn(128 * 197, 384, device=DEV) * 2
+acs = (torch.rand(1, 128, device=DEV) * 0.3 + 0.05)
+acz = torch.randint(0, 8, (1, 128), device=DEV).float()
+ms = timed(lambda: ops.sweep_err_a_self(xa, acs, acz, 4, False))
+res['sweep_err_a_self (128 candidates per element)'] = 4 * xa.numel() / ms / 1e6
+res_extra = {'sweep_err_a_self_ms_25216x384': ms,
+             'sweep_err_a_self_candidate_elements_per_s': 128 * xa.numel() / (ms / 1e3)}
+# exact radix selection (K11): 4 passes over the tensor, 4 B per element and pass
+ranks = torch.tensor([int(0.1 * n), int(0.9 * n), n - 1], device=DEV)
+ms = timed(lambda: ops.select_kth(x.view(1, -1), ranks), 3)
+res['select_kth (4 radix passes, 16 B / element)'] = 16 * n / ms / 1e6
+res_extra['select_kth_ms_77M'] = ms
+ms = timed(lambda: x.view(-1).sort(), 3)
+res_extra['torch_sort_ms_77M'] = ms
 for k, v in res.items():
     print(f'{k:42s} {v:8.0f} GB/s algorithmic  = {100 * v / peak:5.1f}% of measured HBM peak ({peak:.0f} GB/s)')
-json.dump(dict(peak_gbs=peak, achieved_gbs=res), open(os.path.join(ROOT, 'gpurun_out', 'hbm_probe.json'), 'w'), indent=1)
+print(res_extra)
+json.dump(dict(peak_gbs=peak, achieved_gbs=res, extra=res_extra), open(os.path.join(ROOT, 'gpurun_out', 'hbm_probe.json'), 'w'), indent=1)
