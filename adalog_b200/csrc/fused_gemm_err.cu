@@ -78,7 +78,7 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
   float* lut = reinterpret_cast<float*>(sB + (size_t)a.KB * a.BN * 128);   // GEN_LOG: [128][2n + 1]
   __shared__ Tail tl;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int kProdWarp0 = kEpiWarp0 + a.epi_warps;
   const int kProdThreads = (kWorkWarps - a.epi_warps) * 32;
@@ -165,12 +165,16 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && n_units > 0) {
+    // all 32 lanes run this loop converged; one elected lane issues each K block's tcgen05 instructions in a single
+    // asm block (umma_kblock_commit, tc_common.cuh: the one-lane form cost ~17 SASS instructions per MMA, more than
+    // the 104 clocks an N = 208, K = 16 MMA takes -- the issuing warp, not TMEM, bounded this kernel)
+    if (n_units > 0) {
       const uint32_t idesc = I8 ? make_idesc_i8(a.BN) : make_idesc(a.BN);
       const uint32_t blk = (uint32_t)a.BN * 128u;
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       mbar_wait(&tl.bfull, 0);
       // ring positions advance incrementally: a division by a run-time stage count is a dependent chain of ~25
-      // instructions, and four of them per unit sat on the single issuing thread's critical path
+      // instructions, and four of them per unit sat on the issuing warp's critical path
       uint32_t as = 0, aphase = 0, st = 0, sphase = 0;
       for (int t = 0; t < n_units; ++t) {
         mbar_wait(&tl.tempty[as], aphase ^ 1);
@@ -178,20 +182,14 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * a.acc_cols;
         for (int kb = 0; kb < a.KB; ++kb) {
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)(st * a.KB + kb) * kABlock));
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)kb * blk));
-          // UMMA_K = 16 bf16 / 32 int8 = 32 bytes; K slices that are all padding are skipped
+          // UMMA_K = 16 bf16 / 32 int8 = 32 bytes; K slices that are all padding are skipped.  The last block's
+          // commit frees the candidate tile once these MMAs retire.
           const int ks = min(4, (a.K - kb * EL + EL / 4 - 1) / (EL / 4));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < ks) {
-              if (I8) umma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-          }
+          umma_kblock_commit<I8>(tmem_d, make_smem_desc(sA_u + (uint32_t)(st * a.KB + kb) * kABlock),
+                                 make_smem_desc(sB_u + (uint32_t)kb * blk), idesc, kb != 0 ? 1u : 0u, ks,
+                                 kb == a.KB - 1 ? smem_u32(&tl.afree[st]) : 0u);
         }
-        umma_commit(&tl.afree[st]);      // the candidate tile may be overwritten once these MMAs retire
-        umma_commit(&tl.tfull[as]);      // accumulator ready for the epilogue
+        umma_commit_elect(smem_u32(&tl.tfull[as]));      // accumulator ready for the epilogue
         if (++as == (uint32_t)a.nacc) { as = 0; aphase ^= 1; }
         if (++st == (uint32_t)a.nst) { st = 0; sphase ^= 1; }
       }

@@ -89,7 +89,7 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __shared__ SmemTail tail_s;
   SmemTail* tail = &tail_s;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   // static work list of this CTA.  Logical coordinates (bx = unit list, by = N-tile split) come off a 1-D grid in
@@ -147,9 +147,12 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // all 32 lanes run this loop converged; one elected lane issues the K block's tcgen05 instructions in a single asm
+    // block (umma_kblock_commit, tc_common.cuh: the one-lane form cost ~17 SASS instructions per MMA)
+    {
       uint32_t stage = 0, phase = 0;
       const uint32_t idesc = I8 ? make_idesc_i8(a.BN) : make_idesc(a.BN);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       for (int t = 0; t < n_tiles; ++t) {
         const uint32_t as = t & 1, aphase = (t >> 1) & 1;
         mbar_wait(&tail->tempty[as], aphase ^ 1);
@@ -158,17 +161,13 @@ cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < a.KB; ++kb) {
           mbar_wait(&tail->full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)stage * kABytes));
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * kBBytes));
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) { // UMMA_K = 16 bf16 or 32 int8 = 32 bytes -> +2 in the (addr>>4) field
-            if (I8) umma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&tail->empty[stage]);    // frees the smem slot when these MMAs retire
+          // UMMA_K = 16 bf16 or 32 int8 = 32 bytes -> +2 in the (addr>>4) field per K slice; the commit frees the
+          // smem slot when these MMAs retire
+          umma_kblock_commit<I8>(tmem_d, make_smem_desc(sA_u + stage * kABytes), make_smem_desc(sB_u + stage * kBBytes),
+                                 idesc, kb != 0 ? 1u : 0u, 4, smem_u32(&tail->empty[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tail->tfull[as]);         // accumulator ready for the epilogue
+        umma_commit_elect(smem_u32(&tail->tfull[as]));         // accumulator ready for the epilogue
       }
     }
   } else if (warp < kTmaWarp) {

@@ -43,17 +43,20 @@ constexpr int kProdWarps = 12;
 constexpr int kEpiWarps = 8;                          // two per TMEM lane quadrant: column groups eg = 0 / 1 take alternate slabs
 // Warp order = issue priority (the arbiter favours the highest warp id of a scheduler): producers lowest, then the
 // epilogue, and the two single-lane control warps on top.
-// 22 warps x 80 registers: the generation is latency bound per warp (dependent FMA chains, LUT loads), so the producers
+// 23 warps x 80 registers (the register file is allocated in 512-register units per warp: 23 x 2560): the generation is latency bound per warp (dependent FMA chains, LUT loads), so the producers
 // get as many warps as the register file allows; the epilogue reads TMEM in 16-column pieces to fit the same budget.
 constexpr int kProdWarp0 = 0;
 constexpr int kEpiWarp0 = kProdWarp0 + kProdWarps;    // 12..19: TMEM lane quadrant = warp % 4, two warps per quadrant
 constexpr int kTmaWarp = kEpiWarp0 + kEpiWarps;       // 20: TMA of the fixed operand
 constexpr int kMmaWarp = kTmaWarp + 1;                // 21: MMA issuer + TMEM allocator
-constexpr int kThreads = (kMmaWarp + 1) * 32;         // 704
+constexpr int kRelayWarp = kMmaWarp + 1;              // 22: turns "accumulator full" mbarrier phases into named-barrier arrivals
+constexpr int kThreads = (kRelayWarp + 1) * 32;       // 736
+constexpr int kCPT = 3;                               // candidates per producer thread: cg, cg + 48, cg + 96 (< 128)
+constexpr int kBarTile0 = 3;                          // named barriers 3, 4: accumulator slot 0 / 1 is full
 constexpr int kProdThreads = kProdWarps * 32;         // 384 = 8 chunks x 48 candidate groups
 constexpr int kCandGroups = kProdThreads / 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kMaxSA = 12, kMaxSB = 4, kMaxSlots = 4;
+constexpr int kMaxSA = 12, kMaxSB = 8, kMaxSlots = 4;
 constexpr uint32_t kATile = kBM * 128;                // one K block of the candidate tile: 128 rows x 128 bytes
 constexpr uint32_t kTmemCols = 512;
 
@@ -66,6 +69,7 @@ struct __align__(16) Tail {
   float mt[64];
   double comb[kBM];            // sums of column group 1, folded into group 0's at the end
   float lim_min;
+  uint32_t lut_bias[kCPT];     // AdaLog: LUT base of this thread's i-th candidate minus 4 * bits(1.5*2^23), see the producers
   uint32_t tmem_base;
   uint64_t afull[kMaxSA], afree[kMaxSA], bfull[kMaxSB], bfree[kMaxSB], tfull[kMaxSlots], tempty[kMaxSlots];
 };
@@ -87,8 +91,10 @@ enum { GEN_UNIFORM = 0, GEN_LOG = 1 };
 // for ~1e-4 of the chunks and returns its 8 values already packed (four bf16x2 words, in registers): an array parameter
 // in local memory would drag the fast path's registers through the stack as well (measured: STL/LDL per candidate in
 // the hot loop).
-__device__ __noinline__ uint4 log_chunk_slow(const float* __restrict__ xsrc, int n_valid, float sh, bool shifted, float s,
-                                             float qf, const float* mt, float ncode) {
+__device__ __noinline__ uint4 log_chunk_slow(const float* __restrict__ x, long long ldx, int u, int kc, int K, float sh,
+                                             bool shifted, float s, float qf, const float* mt, float ncode) {
+  const float* xsrc = x + (long long)u * ldx + kc;           // (computed here: the hot loop would otherwise carry it)
+  const int n_valid = min(8, K - kc);
   uint32_t o[4];
   for (int j2 = 0; j2 < 4; ++j2) {
     float v2[2];
@@ -106,6 +112,26 @@ __device__ __noinline__ uint4 log_chunk_slow(const float* __restrict__ xsrc, int
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// IEEE path of a uniform chunk (uq_int: the reference's own operation order), out of line for the same reason; the
+// chunk's source values are re-read from their shared-memory staging row.
+template <bool I8>
+__device__ __noinline__ uint4 uq_chunk_slow(uint32_t src_s, float s, float z, float L) {
+  uint32_t o[4];
+  for (int w = 0; w < 4; ++w) {
+    if (I8) {
+      float4 x4;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x4.x), "=f"(x4.y), "=f"(x4.z), "=f"(x4.w)
+                   : "r"(src_s + (uint32_t)w * 16u));
+      o[w] = pack_i8x4(uq_int(x4.x, s, z, L), uq_int(x4.y, s, z, L), uq_int(x4.z, s, z, L), uq_int(x4.w, s, z, L));
+    } else {
+      float x0, x1;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(src_s + (uint32_t)w * 8u));
+      o[w] = pack_bf16x2(uq_int(x0, s, z, L), uq_int(x1, s, z, L));
+    }
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <int GEN, bool I8>
 __global__ void __maxnreg__(80)
 lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
@@ -117,9 +143,11 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
   float* lut = reinterpret_cast<float*>(sB + (size_t)a.SB * bstage);   // GEN_LOG: [128][2n + 1]
   // the unit's K source values, staged once per generation: x (uniform) or -log2(x + shift) (AdaLog)
   float* srcs = lut + (GEN == GEN_LOG ? ADALOG_P * (2 * a.nl + 1) : 0);
+  // per 16-byte chunk of the staged row: the element part of the rounding margin (+inf: the chunk takes the IEEE path)
+  float* chunk_g = srcs + a.KB * (GEN == GEN_LOG ? 64 : (I8 ? 128 : 64));
   __shared__ Tail tl;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   constexpr int EL = I8 ? 128 : 64;        // elements per 128-byte K block
   constexpr int EPT = I8 ? 16 : 8;         // elements per 16-byte chunk
@@ -200,6 +228,7 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
       lut[i] = val;
     }
     if (w == 0) {
+      for (int i = 0; i < kCPT; ++i) tl.lut_bias[i] = smem_u32(lut) - 0x2D000000u + (uint32_t)(i * kCandGroups * lw) * 4u;
       float m = __int_as_float(0x7f800000);
       for (int p = 0; p < ADALOG_P; ++p) m = fminf(m, tl.cand[p].z);
       tl.lim_min = m;
@@ -220,18 +249,25 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
           for (int kb = 0; kb < a.KB; ++kb)
             for (int j = 0; j < a.G; ++j) {
               mbar_wait(&tl.bfree[bs], bph ^ 1);
-              mbar_expect_tx(&tl.bfull[bs], bstage);
-              tma_load_2d(&tmB, &tl.bfull[bs], sB + (size_t)bs * bstage, kb * EL, (g * a.G + j) * a.BN);
+              if ((a.dbg & 16) && ((kb + j) & 1)) {            // diagnostic: every other box is not loaded (wrong results)
+                mbar_arrive(&tl.bfull[bs]);
+              } else {
+                mbar_expect_tx(&tl.bfull[bs], bstage);
+                tma_load_2d(&tmB, &tl.bfull[bs], sB + (size_t)bs * bstage, kb * EL, (g * a.G + j) * a.BN);
+              }
               if (++bs == (uint32_t)a.SB) { bs = 0; bph ^= 1; }
             }
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // All 32 lanes run this loop converged; the tcgen05 instructions of a K block are issued by one elected lane in a
+    // single asm block (umma_kblock_commit, tc_common.cuh).
+    {
       const uint32_t idesc = I8 ? make_idesc_i8(a.BN) : make_idesc(a.BN);
+      const int last_ks = min(4, (a.K - (a.KB - 1) * EL + EL / 4 - 1) / (EL / 4));   // live K slices of the last block
       uint32_t as0 = 0, aph0 = 0;          // ring position of the current generation's K block 0
       uint32_t bs = 0, bph = 0, tj = 0;
-      const int last_ks = min(4, (a.K - (a.KB - 1) * EL + EL / 4 - 1) / (EL / 4));   // live K slices of the last block
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       for (int u = 0; u < n_units; ++u) {
         for (int g = 0; g < a.NG; ++g) {
           const bool a_first = a.streamed || g == 0;
@@ -239,32 +275,32 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
           uint32_t as = as0, aph = aph0;
           for (int kb = 0; kb < a.KB; ++kb) {
             if (a_first) mbar_wait(&tl.afull[as], aph);
-            const int ks = kb == a.KB - 1 ? last_ks : 4;
-            const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)as * kATile));
+            const uint64_t adesc = make_smem_desc(sA_u + as * kATile);
             for (int j = 0; j < a.G; ++j) {
               const uint32_t t = tj + j, ts = t & 1;
               if (kb == 0) mbar_wait(&tl.tempty[ts], ((t >> 1) & 1) ^ 1);
               mbar_wait(&tl.bfull[bs], bph);
               tc_fence_after();
-              const uint32_t tmem_d = tmem_base + ts * 256u;
-              const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)bs * bstage));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ks) {
-                  if (I8) umma_i8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                  else    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                }
-              }
-              umma_commit(&tl.bfree[bs]);
+              umma_kblock_commit<I8>(tmem_base + ts * 256u, adesc, make_smem_desc(sB_u + bs * bstage), idesc,
+                                     kb != 0 ? 1u : 0u, kb == a.KB - 1 ? last_ks : 4, smem_u32(&tl.bfree[bs]));
               if (++bs == (uint32_t)a.SB) { bs = 0; bph ^= 1; }
             }
-            if (a_last) umma_commit(&tl.afree[as]);
+            if (a_last) umma_commit_elect(smem_u32(&tl.afree[as]));
             if (++as == (uint32_t)a.SA) { as = 0; aph ^= 1; }
           }
-          for (int j = 0; j < a.G; ++j) umma_commit(&tl.tfull[(tj + j) & 1]);
+          for (int j = 0; j < a.G; ++j) umma_commit_elect(smem_u32(&tl.tfull[(tj + j) & 1]));
           tj += a.G;
           if (a_last) { as0 = as; aph0 = aph; }
         }
+      }
+    }
+  } else if (warp == kRelayWarp) {
+    // ===================== relay: tfull mbarrier phase -> named-barrier arrival (one polling warp instead of eight) ====
+    if (!(a.dbg & 4)) {
+      const int n_jobs = n_units * a.NT;
+      for (int t = 0; t < n_jobs; ++t) {
+        mbar_wait(&tl.tfull[t & 1], ((uint32_t)t >> 1) & 1);
+        asm volatile("bar.arrive %0, %1;" ::"r"(kBarTile0 + (t & 1)), "n"(kEpiThreads + 32) : "memory");
       }
     }
   } else if (warp >= kEpiWarp0 && warp < kTmaWarp) {
@@ -323,7 +359,11 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
       for (int i = 0; i < kSlabs; ++i) { ysw[i * 32 + lane] = yreg[i]; csw[i * 32 + lane] = creg[i]; }
       __syncwarp();
       if (t + 1 < n_jobs) load_y(cu, cnt);   // consumed at the top of the next iteration
-      mbar_wait_sleep(&tl.tfull[ts], ((uint32_t)t >> 1) & 1, nap);
+      // "slot ts is full": the relay warp watches the mbarrier and arrives on a named barrier, so that the eight
+      // epilogue warps block in hardware instead of polling (ncu, AdaLog fc2 sweep: the nanosleep poll loop of these
+      // warps came back every ~45 clocks and was 47% of all executed warp instructions)
+      if (a.dbg & 4) mbar_wait_sleep(&tl.tfull[ts], ((uint32_t)t >> 1) & 1, nap);
+      else asm volatile("bar.sync %0, %1;" ::"r"(kBarTile0 + (int)ts), "n"(kEpiThreads + 32) : "memory");
       tc_fence_after();
       acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.0f;
       const uint32_t tbase = tmem_base + lane_base + ts * 256u;
@@ -352,12 +392,33 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
     if (eg == 0) a.partial[(long long)blockIdx.x * kBM + et] = acc64 + tl.comb[et];
   } else {
     // ===================== producers: K-block tiles of the candidate operand, straight into swizzled smem =====================
-    // thread -> 16-byte chunk ch of the row, candidates cg, cg + 24, cg + 48, ... (< 128)
+    // thread -> 16-byte chunk ch of the row, candidates p_i = cg + 48 i (i < 3, p_i < 128).  The candidates of a
+    // thread never change, so their constants, LUT rows and store offsets live in registers for the whole kernel.
     const int w = threadIdx.x - kProdWarp0 * 32;
     const int ch = w & 7, cg = w >> 3;
-    const uint32_t c_in = (uint32_t)ch;
     const int lw = 2 * a.nl + 1;
-    const uint32_t lut_bias = smem_u32(lut) - 0x2D000000u;    // addr = bits(t + 1.5*2^23) * 4 + lut_bias (mod 2^32)
+    // AdaLog LUT address = bits(code + row + 1.5*2^23) * 4 + lut_bias (mod 2^32); the row of candidate i is
+    // (cg + 48 i) lw: the cg part rides in the rounding constant kw, the 48 i part in the (uniform) bias -- read back
+    // from shared memory so that ptxas cannot split the constant off again (it rematerialised shift + two adds per
+    // element instead of ONE LEA when the value was computed in registers)
+    const uint32_t lb0 = tl.lut_bias[0], lb1 = tl.lut_bias[1], lb2 = tl.lut_bias[2];
+    uint32_t srcs_s = smem_u32(srcs), sA_s = smem_u32(sA);
+    asm volatile("" : "+r"(srcs_s), "+r"(sA_s));              // (ptxas otherwise rematerialises the aligned smem base per store)
+    float kx[kCPT], ky[kCPT], kw[kCPT], kt[kCPT];
+#pragma unroll
+    for (int i = 0; i < kCPT; ++i) {
+      const int p = min(cg + i * kCandGroups, ADALOG_P - 1);
+      const float4 c = tl.cand[p];
+      kx[i] = c.x; ky[i] = c.y; kt[i] = tl.cthr[p];
+      // uniform: 1.5*2^23 - zp;  AdaLog: 1.5*2^23 + cg lw for all three, so that the bits of the rounded value index
+      // the LUT directly (exact ties, where the parity of this constant would matter, always take the IEEE path)
+      kw[i] = GEN == GEN_LOG ? kMagic + (float)(cg * lw) : c.w;
+    }
+    // row p = cg + 48 i of the tile: 128 bytes per row, chunk position swizzled by p & 7 == cg & 7 (48 % 8 == 0)
+    const uint32_t so0 = (uint32_t)cg * 128u + (((uint32_t)ch ^ ((uint32_t)cg & 7u)) << 4);
+    constexpr uint32_t kSoStep = (uint32_t)kCandGroups * 128u;
+    const bool has3 = cg + 2 * kCandGroups < ADALOG_P;         // warp-uniform: cg = 4 consecutive values per warp
+    const float Lq = (float)(2 * a.nl - 1) / ncode_f;          // uniform: upper clamp L / 2n
     const float lim_min = GEN == GEN_LOG ? tl.lim_min : 0.0f;
     const int n_gen = n_units * gen_per_unit;                 // (unit, pass) pairs
     uint32_t as = 0, aph = 0;
@@ -365,127 +426,110 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
       const int u = u0 + (a.streamed ? gi / a.NG : gi);
       {
         // The unit's K source values, once per generation, shared by all producer threads through shared memory:
-        // uniform: x itself (each thread would otherwise prefetch its chunk into 16 registers);  AdaLog:
-        // -log2(x + shift) with the reference's full-precision log2f (~30 instructions) ONCE per element instead of
-        // once per (element, candidate group) -- the first version spent 40% of the producers' instructions there.
+        // uniform: x itself;  AdaLog: -log2(x + shift) with the reference's full-precision log2f (~30 instructions)
+        // ONCE per element instead of once per (element, candidate group).  Elements beyond K are staged as a benign
+        // finite value: whatever they generate meets the zero K padding of the fixed operand.
+        // Per 16-byte chunk, also once per generation: the element part of the rounding margin --
+        //   AdaLog: (6e-7 max|lx| + 2e-7) 2n, or +inf when an element sits near the reference's 1e-15 clamp, x <= 0 or NaN;
+        //   uniform: +inf when the chunk holds a NaN (FFMA.SAT turns it into 0), else 0
+        // -- so the inner loops test ONE threshold per (candidate, chunk) and +inf routes the chunk to the IEEE path.
         asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads) : "memory");      // everybody is done with the previous unit's values
         const float* xrow = a.x + (long long)u * a.ldx;
         for (int k = w; k < a.KB * EL; k += kProdThreads) {
           float v = GEN == GEN_LOG ? 1.0f : 0.0f;
           if (k < a.K) { v = __ldg(xrow + k); if (GEN == GEN_LOG && a.shift) v = __fadd_rn(v, sh); }
-          srcs[k] = GEN == GEN_LOG ? -log2f(v) : v;
+          const float sv = GEN == GEN_LOG ? -log2f(v) : v;
+          srcs[k] = sv;
+          const float inf = __int_as_float(0x7f800000);
+          float g = GEN == GEN_LOG ? (!(sv <= lim_min) ? inf : fabsf(sv)) : (sv != sv ? inf : 0.0f);
+#pragma unroll
+          for (int m = 1; m < EPT; m <<= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, m));
+          if ((lane & (EPT - 1)) == 0) chunk_g[k / EPT] = GEN == GEN_LOG ? fmaf(6e-7f, g, 2e-7f) * ncode_f : g;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads) : "memory");
       }
       for (int kb = 0; kb < a.KB; ++kb) {
-        const uint32_t a_tile = smem_u32(sA) + as * kATile;
+        const uint32_t a_tile = sA_s + as * kATile + so0;
         const int kc = kb * EL + ch * EPT;
         const bool live = kc < a.K;                           // chunks beyond K are written as zeros
-        const bool tail = kc + EPT > a.K;
         float xv[EPT];
 #pragma unroll
-        for (int j = 0; j < EPT; j += 4) {
-          const float4 v4 = *reinterpret_cast<const float4*>(&srcs[kc + j]);
-          xv[j] = v4.x; xv[j + 1] = v4.y; xv[j + 2] = v4.z; xv[j + 3] = v4.w;
-        }
-        mbar_wait_sleep(&tl.afree[as], aph ^ 1, 200u);   // the MMAs that read this stage have retired
-        auto store = [&](int p, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {
-          const uint32_t addr = a_tile + (uint32_t)p * 128u + ((c_in ^ ((uint32_t)p & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+        for (int j = 0; j < EPT; j += 4)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(xv[j]), "=f"(xv[j + 1]), "=f"(xv[j + 2]), "=f"(xv[j + 3]) : "r"(srcs_s + (uint32_t)(kc + j) * 4u));
+        const float gch = chunk_g[kc / EPT];
+        if (a.dbg & 8) mbar_wait_sleep(&tl.afree[as], aph ^ 1, 200u);
+        else mbar_wait(&tl.afree[as], aph ^ 1);              // the MMAs that read this stage have retired
+        auto store = [&](int i, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3) {      // i: compile-time after unrolling
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_tile + (uint32_t)i * kSoStep), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
         };
         if (a.dbg & 1) {
           // diagnostic: no generation (pipeline cost only)
         } else if (!live) {
           // a chunk beyond K (partial last block): the ring stage may hold another block's data from its last use
-          for (int p = cg; p < ADALOG_P; p += kCandGroups) store(p, 0u, 0u, 0u, 0u);
-        } else if (GEN == GEN_UNIFORM) {
-          int nan_flag = 0;
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) nan_flag |= (xv[j] != xv[j]) ? 1 : 0;
-          asm volatile("" : "+r"(nan_flag));
-          const float L = (float)(2 * a.nl - 1);
-          auto u_gen = [&](int p, float (&tm)[EPT]) {
-            const float4 c = tl.cand[p];
-            const float thr = tl.cthr[p];
+          for (int i = 0; i < kCPT; ++i) if (i < 2 || has3) store(i, 0u, 0u, 0u, 0u);
+        } else if (GEN == GEN_UNIFORM) {
+          // uq_code_fast (quant_device.cuh) on two elements per packed FP32 instruction; tm = (code - zp) + 1.5*2^23
+          auto u_gen = [&](int i) -> uint4 {
             // distance to the rounded value of every element, reduced by a max TREE (a chain of `unsafe |= ...`
             // compiles to EPT serially dependent FSETPs); d is finite: ts is saturated to [0, 1]
-            float dm[EPT];
+            float tm[EPT], dm[EPT];
 #pragma unroll
             for (int j = 0; j < EPT; j += 2) {
-              // uq_code_fast (quant_device.cuh) on two elements per packed FP32 instruction
-              const float ts0 = fminf(__saturatef(fmaf(xv[j], c.x, c.y)), c.z);
-              const float ts1 = fminf(__saturatef(fmaf(xv[j + 1], c.x, c.y)), c.z);
+              const float ts0 = fminf(__saturatef(fmaf(xv[j], kx[i], ky[i])), Lq);
+              const float ts1 = fminf(__saturatef(fmaf(xv[j + 1], kx[i], ky[i])), Lq);
               float n0, n1;
-              ffma2(tm[j], tm[j + 1], ts0, ts1, ncode_f, ncode_f, c.w, c.w);      // (code - zp) + 1.5*2^23
-              fadd2(n0, n1, c.w, c.w, -tm[j], -tm[j + 1]);                        // -(rounded clamped value)
-              ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);        // clamped - rint(clamped)
+              ffma2(tm[j], tm[j + 1], ts0, ts1, ncode_f, ncode_f, kw[i], kw[i]);      // (code - zp) + 1.5*2^23
+              fadd2(n0, n1, kw[i], kw[i], -tm[j], -tm[j + 1]);                        // -(rounded clamped value)
+              ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);            // clamped - rint(clamped)
             }
 #pragma unroll
             for (int w2 = EPT / 2; w2 > 0; w2 >>= 1) {
 #pragma unroll
               for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
             }
-            if (!(dm[0] <= thr) || nan_flag != 0) {           // rare: redo the chunk on the IEEE path
-              const float2 sz = tl.cand_sz[p];
-#pragma unroll
-              for (int j = 0; j < EPT; ++j) tm[j] = __fadd_rn(uq_int(xv[j], sz.x, sz.y, L), kMagic);
+            if (!(fmaxf(dm[0], gch) <= kt[i])) {              // rare: redo the chunk on the IEEE path (out of line)
+              const float2 sz = tl.cand_sz[min(cg + i * kCandGroups, ADALOG_P - 1)];
+              return uq_chunk_slow<I8>(srcs_s + (uint32_t)kc * 4u, sz.x, sz.y, (float)(2 * a.nl - 1));
             }
-            if (tail) {
-#pragma unroll
-              for (int j = 0; j < EPT; ++j) if (kc + j >= a.K) tm[j] = kMagic;
-            }
+            if (I8)
+              return make_uint4(pack_i8x4_bits(tm[0], tm[1], tm[2], tm[3]), pack_i8x4_bits(tm[4], tm[5], tm[6], tm[7]),
+                                pack_i8x4_bits(tm[8 % EPT], tm[9 % EPT], tm[10 % EPT], tm[11 % EPT]),
+                                pack_i8x4_bits(tm[12 % EPT], tm[13 % EPT], tm[14 % EPT], tm[15 % EPT]));
+            return make_uint4(pack_bf16x2(__fsub_rn(tm[0], kMagic), __fsub_rn(tm[1], kMagic)),
+                              pack_bf16x2(__fsub_rn(tm[2], kMagic), __fsub_rn(tm[3], kMagic)),
+                              pack_bf16x2(__fsub_rn(tm[4 % EPT], kMagic), __fsub_rn(tm[5 % EPT], kMagic)),
+                              pack_bf16x2(__fsub_rn(tm[6 % EPT], kMagic), __fsub_rn(tm[7 % EPT], kMagic)));
           };
-          auto u_store = [&](int p, const float (&tm)[EPT]) {
-            if (I8) {
-              store(p, pack_i8x4_bits(tm[0], tm[1], tm[2], tm[3]), pack_i8x4_bits(tm[4], tm[5], tm[6], tm[7]),
-                    pack_i8x4_bits(tm[8 % EPT], tm[9 % EPT], tm[10 % EPT], tm[11 % EPT]),
-                    pack_i8x4_bits(tm[12 % EPT], tm[13 % EPT], tm[14 % EPT], tm[15 % EPT]));
-            } else {
-              store(p, pack_bf16x2(__fsub_rn(tm[0], kMagic), __fsub_rn(tm[1], kMagic)),
-                    pack_bf16x2(__fsub_rn(tm[2], kMagic), __fsub_rn(tm[3], kMagic)),
-                    pack_bf16x2(__fsub_rn(tm[4 % EPT], kMagic), __fsub_rn(tm[5 % EPT], kMagic)),
-                    pack_bf16x2(__fsub_rn(tm[6 % EPT], kMagic), __fsub_rn(tm[7 % EPT], kMagic)));
+#pragma unroll
+          for (int i = 0; i < kCPT; ++i) {
+            if (i < 2 || has3) {
+              const uint4 o = u_gen(i);
+              store(i, o.x, o.y, o.z, o.w);
             }
-          };
-          for (int p = cg; p < ADALOG_P; p += kCandGroups) {
-            float ta[EPT];
-            u_gen(p, ta);
-            u_store(p, ta);
           }
         } else {
           // post-GELU AdaLog search form (linear.py:872-878, :913-919): see gen_log_cand_lut_kernel (quant_kernels.cu)
           // for the derivation of the exact fast path; same arithmetic, same margins, same IEEE fallback.  xv = lx here.
-          // element part of the rounding margin, 6e-7 |lx| + 2e-7 (quant_kernels.cu): the chunk's LARGEST is used for
-          // all of its elements -- conservative (a few more chunks take the IEEE path, still ~1e-4 of them), and the
-          // per-element check shrinks to |d| <= 0.5 - candidate margin - gmax * mul
-          float gmax = 0.0f;
-          bool clamp_region = false;
-#pragma unroll
-          for (int j = 0; j < EPT; ++j) {
-            gmax = fmaxf(gmax, fabsf(xv[j]));
-            clamp_region |= !(xv[j] <= lim_min);              // near the reference's 1e-15 clamp, x <= 0 or NaN
-          }
-          gmax = 6e-7f * gmax + 2e-7f;
-          int clamp_flag = clamp_region ? 1 : 0;
-          asm volatile("" : "+r"(clamp_flag));
-          auto l_gen = [&](int p) -> uint4 {
-            const float4 c = tl.cand[p];
-            const float half = tl.cthr[p];
-            uint32_t row = lut_bias + (uint32_t)(p * lw) * 4u;
-            asm volatile("" : "+r"(row));
+          // The chunk's LARGEST element margin (gch, staged above) is used for all of its elements -- conservative (a
+          // few more chunks take the IEEE path, still ~1e-4 of them) -- so the per-element check shrinks to
+          // |d| <= 0.5 - candidate margin - gch * mul / 2n.
+          auto l_gen = [&](int i) -> uint4 {
             float dm[EPT], v[EPT];
-            const float lim_d = fmaf(-gmax, c.w, half);
+            const float lim_d = fmaf(-gch, kx[i], kt[i]);
+            const uint32_t lb = i == 0 ? lb0 : (i == 1 ? lb1 : lb2);
 #pragma unroll
             for (int j = 0; j < EPT; j += 2) {
-              const float ts0 = __saturatef(fmaf(xv[j], c.x, c.y));
-              const float ts1 = __saturatef(fmaf(xv[j + 1], c.x, c.y));
+              const float ts0 = __saturatef(fmaf(xv[j], kx[i], ky[i]));
+              const float ts1 = __saturatef(fmaf(xv[j + 1], kx[i], ky[i]));
               float tm0, tm1, n0, n1;
-              ffma2(tm0, tm1, ts0, ts1, ncode_f, ncode_f, kMagic, kMagic);
-              fadd2(n0, n1, kMagic, kMagic, -tm0, -tm1);
+              ffma2(tm0, tm1, ts0, ts1, ncode_f, ncode_f, kw[i], kw[i]);              // code + LUT row + 1.5*2^23
+              fadd2(n0, n1, kw[i], kw[i], -tm0, -tm1);
               ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);
               float val0, val1;
-              asm("ld.shared.f32 %0, [%1];" : "=f"(val0) : "r"(__float_as_uint(tm0) * 4u + row));
-              asm("ld.shared.f32 %0, [%1];" : "=f"(val1) : "r"(__float_as_uint(tm1) * 4u + row));
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val0) : "r"(__float_as_uint(tm0) * 4u + lb));
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val1) : "r"(__float_as_uint(tm1) * 4u + lb));
               v[j] = val0; v[j + 1] = val1;
             }
 #pragma unroll
@@ -493,29 +537,23 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
 #pragma unroll
               for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
             }
-            if (!(dm[0] <= lim_d) || clamp_flag != 0) {
-              const float2 qs = tl.cand_sz[p];
-              return log_chunk_slow(a.x + (long long)u * a.ldx + kc, min(EPT, a.K - kc), sh, a.shift != nullptr, qs.y, qs.x,
-                                    tl.mt, ncode_f);
-            }
-            if (tail) {
-#pragma unroll
-              for (int j = 0; j < EPT; ++j) if (kc + j >= a.K) v[j] = 0.0f;
+            if (!(dm[0] <= lim_d)) {
+              const float2 qs = tl.cand_sz[min(cg + i * kCandGroups, ADALOG_P - 1)];
+              return log_chunk_slow(a.x, a.ldx, u, kc, a.K, sh, a.shift != nullptr, qs.y, qs.x, tl.mt, ncode_f);
             }
             return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4 % EPT], v[5 % EPT]),
                               pack_bf16x2(v[6 % EPT], v[7 % EPT]));
           };
           // two candidates per iteration: 2 x EPT independent dependency chains per thread
-          int p = cg;
-          for (; p + kCandGroups < ADALOG_P; p += 2 * kCandGroups) {
-            const uint4 oa = l_gen(p);
-            const uint4 ob = l_gen(p + kCandGroups);
-            store(p, oa.x, oa.y, oa.z, oa.w);
-            store(p + kCandGroups, ob.x, ob.y, ob.z, ob.w);
+          {
+            const uint4 oa = l_gen(0);
+            const uint4 ob = l_gen(1);
+            store(0, oa.x, oa.y, oa.z, oa.w);
+            store(1, ob.x, ob.y, ob.z, ob.w);
           }
-          if (p < ADALOG_P) {
-            const uint4 oa = l_gen(p);
-            store(p, oa.x, oa.y, oa.z, oa.w);
+          if (has3) {
+            const uint4 oa = l_gen(2);
+            store(2, oa.x, oa.y, oa.z, oa.w);
           }
         }
         fence_proxy_async();               // generic-proxy stores -> visible to the tensor core's async proxy
@@ -539,25 +577,29 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
 struct Plan { int KB, BN, NT, G, NG, nslot, slotw, SA, SB, streamed; size_t smem; };
 constexpr size_t kSmemLimit = 227 * 1024 - sizeof(Tail) - 1024;
 
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; }
+
 static int make_plan(const adalog_lin_fused_args* a, Plan* pl) {
+  // tuning overrides (0 = choose): ring depths of the generated (A) and the streamed fixed (B) operand
+  const int want_sa = env_int("ADALOG_B200_LINF_SA", 0), want_sb = env_int("ADALOG_B200_LINF_SB", 0);
   const bool i8 = a->dtype == ADALOG_I8;
   const int EL = i8 ? 128 : 64;
   const bool log = a->gen == ADALOG_GEN_LOG;
   pl->KB = (a->K + EL - 1) / EL;
   // the unit's K staged source values, and for GEN_LOG the per-candidate value LUT
-  const size_t lut = ((log ? (size_t)ADALOG_P * (2 * a->n_levels + 1) : 0) + (size_t)pl->KB * EL) * sizeof(float);
+  const size_t lut = ((log ? (size_t)ADALOG_P * (2 * a->n_levels + 1) : 0) + (size_t)pl->KB * EL + (size_t)pl->KB * 8) * sizeof(float);
   auto r16 = [](int v) { return ((v + 15) / 16) * 16; };
   // RESIDENT: every K block of a unit in shared memory at once, at least one spare stage, at least 2 B stages
   {
     const int nt = (a->N + 255) / 256;
     const int BN = std::min(256, std::max(16, r16((a->N + nt - 1) / nt)));
     const size_t bst = (size_t)BN * 128;
-    for (int SB = 3; SB >= 2; --SB) {
+    for (int SB = want_sb ? std::min(want_sb, kMaxSB) : 3; SB >= 2; --SB) {
       const long long room = (long long)kSmemLimit - (long long)lut - (long long)SB * (long long)bst;
       const int SA = (int)std::min<long long>(kMaxSA, room / (long long)kATile);
       if (SA >= pl->KB + 1) {
         pl->BN = BN; pl->NT = (a->N + BN - 1) / BN; pl->G = 1; pl->NG = pl->NT; pl->nslot = 2; pl->slotw = 256;
-        pl->SA = std::min(SA, 2 * pl->KB); pl->SB = SB; pl->streamed = 0;
+        pl->SA = std::min(SA, want_sa ? std::max(want_sa, pl->KB + 1) : 2 * pl->KB); pl->SB = SB; pl->streamed = 0;
         pl->smem = 1024 + (size_t)pl->SA * kATile + (size_t)SB * bst + lut;
         return 0;
       }
@@ -571,10 +613,10 @@ static int make_plan(const adalog_lin_fused_args* a, Plan* pl) {
     const int BN = std::min(256, std::max(16, r16((per_pass + G - 1) / G)));
     const size_t bst = (size_t)BN * 128;
     pl->BN = BN; pl->G = G; pl->NG = passes; pl->NT = passes * G; pl->nslot = 2; pl->slotw = 256; pl->streamed = 1;
-    for (int SB = 4; SB >= 2; --SB) {
+    for (int SB = want_sb ? std::min(want_sb, kMaxSB) : 4; SB >= 2; --SB) {
       const long long room = (long long)kSmemLimit - (long long)lut - (long long)SB * (long long)bst;
-      const int SA = (int)std::min<long long>(6, room / (long long)kATile);
-      if (SA >= 3) {
+      const int SA = (int)std::min<long long>(want_sa ? want_sa : 6, room / (long long)kATile);
+      if (SA >= (want_sa ? 2 : 3)) {
         pl->SA = SA; pl->SB = SB;
         pl->smem = 1024 + (size_t)SA * kATile + (size_t)SB * bst + lut;
         return 0;
@@ -616,7 +658,7 @@ static int launch(const adalog_lin_fused_args* a, cudaStream_t st) {
   k.KB = pl.KB; k.N = a->N; k.BN = pl.BN; k.NT = pl.NT; k.G = pl.G; k.NG = pl.NG; k.nslot = pl.nslot; k.slotw = pl.slotw;
   k.SA = pl.SA; k.SB = pl.SB; k.streamed = pl.streamed;
   k.vec = ((a->ldx & 3) == 0 && (a->K & 3) == 0 && (reinterpret_cast<uintptr_t>(a->x) & 15) == 0) ? 1 : 0;
-  { const char* e = getenv("ADALOG_B200_LINF_DBG"); k.dbg = e ? atoi(e) : 0; }   // diagnostics: 1 = no generation, 2 = no epilogue
+  { const char* e = getenv("ADALOG_B200_LINF_DBG"); k.dbg = e ? atoi(e) : 0; }   // diagnostics: 1 = no generation, 2 = no epilogue, 4 = epilogue polls, 8 = producers poll with nanosleep, 16 = half the B loads
   k.y = a->y; k.ldy = a->ldy; k.rs = a->rs; k.ccs = a->ccs; k.ccb = a->ccb; k.partial = a->partial;
   const bool i8 = a->dtype == ADALOG_I8;
   CUtensorMap tmB;

@@ -124,6 +124,50 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// Lean issue path for a CONVERGED warp (all 32 lanes in lock step, every operand warp-uniform): the four K slices of
+// one 128-byte K block (the descriptor start address advances by 32 bytes = 2 units per slice) followed by the commit
+// of `bar_addr`, issued by one elected lane inside a single asm block.  The one-lane form above (`if (lane == 0)`
+// around umma_* / umma_commit) costs ~17 SASS instructions per MMA: ptxas wraps every tcgen05 instruction of a
+// divergent region in an elect / R2UR / BRA.U.ANY "waterfall" because its operands must sit in uniform registers.
+// ncu on the linear activation sweeps: the issuing warp ran 280 instructions per K block against 768 clocks of MMA
+// work and was never found waiting at a barrier -- the tensor pipe (41-51% active) was bound by this instruction stream.
+template <bool I8>
+__device__ __forceinline__ void umma_kblock_commit(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t acc_first, int ks, uint32_t bar_addr) {
+  // ks = live K slices of this block (1..4; slices that are all K padding are skipped); bar_addr == 0: no commit
+#define ADALOG_UMMA_KBLOCK(KIND)                                                                          \
+  asm volatile(                                                                                           \
+      "{\n\t.reg .pred pe, p0, pt, p1, p2, p3, pc;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"              \
+      "elect.sync _|pe, 0xffffffff;\n\t"                                                                  \
+      "setp.ne.b32 p0, %4, 0;\n\t"                                                                        \
+      "setp.eq.b32 pt, %4, %4;\n\t"                                                                       \
+      "setp.gt.and.s32 p1, %5, 1, pe;\n\t"                                                                \
+      "setp.gt.and.s32 p2, %5, 2, pe;\n\t"                                                                \
+      "setp.gt.and.s32 p3, %5, 3, pe;\n\t"                                                                \
+      "setp.ne.and.b32 pc, %6, 0, pe;\n\t"                                                                \
+      "add.s64 a1, %1, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 a3, %1, 6;\n\t"                                \
+      "add.s64 b1, %2, 2;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 b3, %2, 6;\n\t"                                \
+      "@pe tcgen05.mma.cta_group::1.kind::" KIND " [%0], %1, %2, %3, p0;\n\t"                              \
+      "@p1 tcgen05.mma.cta_group::1.kind::" KIND " [%0], a1, b1, %3, pt;\n\t"                              \
+      "@p2 tcgen05.mma.cta_group::1.kind::" KIND " [%0], a2, b2, %3, pt;\n\t"                              \
+      "@p3 tcgen05.mma.cta_group::1.kind::" KIND " [%0], a3, b3, %3, pt;\n\t"                              \
+      "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}"              \
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc_first), "r"(ks), "r"(bar_addr)          \
+      : "memory")
+  if (I8) ADALOG_UMMA_KBLOCK("i8");
+  else    ADALOG_UMMA_KBLOCK("f16");
+#undef ADALOG_UMMA_KBLOCK
+}
+// commit issued by one elected lane of a converged warp
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar_addr) : "memory");
+}
+// warp index the compiler can prove warp-uniform (so that everything derived from it may live in uniform registers)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
