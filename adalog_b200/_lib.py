@@ -84,6 +84,7 @@ SIGNATURES = {
     'adalog_fused_cand_gemm_err_grid': [ctypes.POINTER(FusedArgs)],
     'adalog_fused_cand_gemm_err': [ctypes.POINTER(FusedArgs), c_vp],
     'adalog_lin_fused_cand_gemm_err_grid': [ctypes.POINTER(LinFusedArgs)],
+    'adalog_lin_fused_cand_gemm_err_passes': [ctypes.POINTER(LinFusedArgs)],
     'adalog_lin_fused_cand_gemm_err': [ctypes.POINTER(LinFusedArgs), c_vp],
     'adalog_gemm_dequant': [ctypes.POINTER(GemmErrArgs), c_vp, c_i64, c_i64, c_vp],
     'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
@@ -96,7 +97,7 @@ _lib = None
 # kernels launched through this binding (bench.py reports it as gpu_launches)
 LAUNCHES = {'count': 0}
 _NO_LAUNCH = {'adalog_version', 'adalog_cand_gemm_err_grid', 'adalog_fused_cand_gemm_err_grid',
-              'adalog_lin_fused_cand_gemm_err_grid'}
+              'adalog_lin_fused_cand_gemm_err_grid', 'adalog_lin_fused_cand_gemm_err_passes'}
 
 
 class AdalogError(RuntimeError):

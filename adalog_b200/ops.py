@@ -430,9 +430,10 @@ def fused_cand_gemm_err(x2d, K, Bm, N, U, UG, brpg, y, ldy, rs, rs_div, rs_mod, 
 
 
 def lin_fused_cand_gemm_err(x2d, Bm, N, y, rs, ccs, ccb, n_levels, P, cs, cz=None, cq=None, shift=None, mtab=None,
-                            i8=False):
+                            i8=False, max_passes=None):
     """One launch of adalog_lin_fused_cand_gemm_err over all tokens of a linear activation sweep.  Returns the FP64
-    partial [grid, 128], or None when no schedule fits in shared memory (caller: two-kernel path)."""
+    partial [grid, 128], or None when no schedule fits in shared memory or the schedule would generate each unit's
+    operand more than `max_passes` times (caller: two-kernel path)."""
     _cuda(x2d, Bm, y, rs, ccs, ccb, cs, cz, cq, shift, mtab)
     assert x2d.dtype == torch.float32 and x2d.stride(1) == 1 and y.stride(1) == 1
     log = cq is not None
@@ -453,6 +454,8 @@ def lin_fused_cand_gemm_err(x2d, Bm, N, y, rs, ccs, ccb, n_levels, P, cs, cz=Non
     lib = _lib.load()
     grid = lib.adalog_lin_fused_cand_gemm_err_grid(ctypes.byref(a))
     if grid == -3 or grid == -2:
+        return None
+    if max_passes is not None and grid > 0 and lib.adalog_lin_fused_cand_gemm_err_passes(ctypes.byref(a)) > max_passes:
         return None
     if grid < 0:
         raise AdalogError(f'adalog_lin_fused_cand_gemm_err_grid failed ({grid}): {lib.adalog_last_error().decode()}')

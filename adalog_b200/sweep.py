@@ -27,25 +27,21 @@ R_BASE = 37.0
 USE_I8 = os.environ.get('ADALOG_B200_I8', '1') == '1'
 
 # linear activation sweeps: generate the candidate operand inside the GEMM kernel (0: generator -> workspace -> GEMM)
-LIN_FUSED = os.environ.get('ADALOG_B200_LIN_FUSED', '1') == '1'
+LIN_FUSED = os.environ.get('ADALOG_B200_LIN_FUSED', '1') != '0'
 
 
-def _use_lin_fused(K, N, log, i8):
-    """Which path scores a linear activation sweep.  Measured on 128 x 197 tokens (tests/gpu_lin_bench.py, fused vs
-    generator -> workspace -> GEMM, ms per evaluation): DeiT-S K=384 int8: N=1152 2.00 vs 2.16, N=1536 2.31 vs 2.36,
-    N=384 1.26 vs 1.17; AdaLog K=1536 N=384 5.1 vs 5.5 (7.7 inside a calibration, where the two kernels of one
-    evaluation overlap less than in a back-to-back loop).  DeiT-B K=768 int8: 5.6 vs 4.8 / 7.9 vs 6.1 and AdaLog K=3072
-    N=768 (two passes that regenerate the operand) 20.5 vs 17.5: with six or more K blocks resident per unit the
-    producers cannot run ahead of the MMAs (one spare stage), and the fixed-operand stream has 3 x 32 KB in flight
-    against 4 x 48 KB of the two-kernel GEMM.  ADALOG_B200_LIN_FUSED=force takes the fused kernel wherever it fits."""
+def _lin_fused_passes():
+    """Policy for the linear activation sweeps: None = generator -> workspace -> GEMM; else the largest number of times
+    the fused kernel may generate a unit's operand.  Measured on 128 x 197 tokens after the lean MMA issuer
+    (tests/gpu_lin_bench.py, fused vs two-kernel, ms per evaluation): DeiT-S int8 K=384: N=1152 1.78 vs 2.15, N=384 1.10
+    vs 1.16, N=1536 2.05 vs 2.36, AdaLog K=1536 N=384 4.08 vs 5.41; DeiT-B int8 K=768: N=2304 4.31 vs 4.93, N=768 2.09
+    vs 2.40, N=3072 5.51 vs 6.47.  Only the schedules that regenerate the operand (DeiT-B AdaLog K=3072 N=768: two
+    512-column TMEM passes, 17.4 vs 16.9) stay on the two-kernel path.  ADALOG_B200_LIN_FUSED=force takes the fused
+    kernel wherever it fits, =0 never."""
     mode = os.environ.get('ADALOG_B200_LIN_FUSED', '1')
     if not LIN_FUSED or mode == '0':
-        return False
-    if mode == 'force':
-        return True
-    if log:
-        return N <= 512                       # one pass: the operand is generated once per unit
-    return (K if i8 else 2 * K) <= 512        # at most four K blocks resident per unit
+        return None
+    return 1 << 30 if mode == 'force' else 1
 
 _workspaces = {}
 
@@ -411,10 +407,10 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a, y2d=None):
     ntok = ctx.x2d.shape[0]
     y = ctx.y2d if y2d is None else y2d
     res = None
-    if out_f % 4 == 0 and _use_lin_fused(in_f, out_f, False, i8):
+    if out_f % 4 == 0 and _lin_fused_passes() is not None:
         # candidates generated inside the GEMM kernel: one launch, nothing expanded in HBM (lin_fused_gemm_err.cu)
         res = ops.lin_fused_cand_gemm_err(ctx.x2d, Bm, out_f, y, rs, s_w.contiguous(), cb.contiguous(), n_levels_a, P,
-                                          c1, cz=z1, i8=i8)
+                                          c1, cz=z1, i8=i8, max_passes=_lin_fused_passes())
     if res is None:
         res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, y, out_f, rs, None, 1 << 62, 1, s_w, cb,
                             k_true=in_f, i8=i8)
@@ -464,9 +460,9 @@ def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
     cb = (b - shift.double() * s_w.double() * colsum.double()).float().contiguous()
     ntok = ctx.x2d.shape[0]
     res = None
-    if out_f % 4 == 0 and _use_lin_fused(in_f, out_f, True, False):
+    if out_f % 4 == 0 and _lin_fused_passes() is not None:
         res = ops.lin_fused_cand_gemm_err(ctx.x2d, Bm, out_f, ctx.y2d, rs, s_w.contiguous(), cb, nl, P, c1, cq=q1,
-                                          shift=shift, mtab=mtab)
+                                          shift=shift, mtab=mtab, max_passes=_lin_fused_passes())
     if res is None:
         res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
                             k_true=in_f)

@@ -213,7 +213,8 @@ int adalog_fused_cand_gemm_err(const adalog_fused_args* a, void* stream);
  * x  [U, K] FP32 (row pitch ldx): the layer input, unit u = token u; candidates are per-tensor:
  *   gen = ADALOG_GEN_UNIFORM: cs[p], cz[p] (scale, zero point);
  *   gen = ADALOG_GEN_LOG: cs[p] (scale), cq[p] (base), shift[0] (post-GELU shift or NULL), mtab[37] search-LUT numerators.
- * Bm [b_rows >= N, KB*64|128]: integer part of the quantised weight (adalog_gen_uniform_fixed), zero padded in K.
+ * Bm [b_rows >= N, KB*64|128]: integer part of the quantised weight (adalog_gen_uniform_fixed); its K padding MUST be
+ *   zero: the candidate side is only kept finite there, not zeroed.
  * yhat[p, n] = rs[p] * ccs[n] * D[p, n];  e[p] += (y[u*ldy + n] - ccb[n] - yhat)^2;  partial[x*128 + p] (FP64), x < grid.
  * N must be a multiple of 4, ccs 16-byte aligned.  Returns -3 when no schedule fits in shared memory (the caller then
  * takes the generator -> workspace -> adalog_cand_gemm_err path). */
@@ -231,6 +232,10 @@ typedef struct {
 } adalog_lin_fused_args;
 
 int adalog_lin_fused_cand_gemm_err_grid(const adalog_lin_fused_args* a);
+/* how often the schedule for this shape generates each unit's candidate operand: 1 when all K blocks of a unit stay in
+ * shared memory or its N columns fit in one 512-column TMEM pass, ceil(N/512) otherwise (the caller may then prefer
+ * the generator -> workspace -> adalog_cand_gemm_err path); negative on error */
+int adalog_lin_fused_cand_gemm_err_passes(const adalog_lin_fused_args* a);
 int adalog_lin_fused_cand_gemm_err(const adalog_lin_fused_args* a, void* stream);
 
 /* ---------------------------------------------------------------- fake-quant INFERENCE forward of a linear layer
