@@ -5,9 +5,10 @@
 // accumulated in a register across the CTA's whole static work list with no cross-thread reduction, which
 // keeps equal candidates bit-equal (exact-tie parity, SURVEY.md section 7 hard part 1).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2-9 = epilogue (TMEM lanes 32*(w%4)..; two column groups).  Pipelines: smem full/empty ring (kStages) between TMA and
-// MMA; TMEM full/empty (2 accumulator stages of 256 columns) between MMA and epilogue.
+// Warp roles (320 threads): warps 0-7 = epilogue (TMEM lanes 32*(w%4)..; two column groups), warp 8 = TMA producer,
+// warp 9 = TMEM allocator + MMA issuer (the whole warp runs the issue loop converged, one elected lane issues each K
+// block's tcgen05 instructions in a single asm block: tc_common.cuh umma_kblock_commit).  Pipelines: smem full/empty
+// ring (kStages) between TMA and MMA; TMEM full/empty (2 accumulator stages of 256 columns) between MMA and epilogue.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/adalog_b200.h"

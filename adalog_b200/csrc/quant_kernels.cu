@@ -525,10 +525,24 @@ __global__ void __launch_bounds__(256, 4) gen_uniform_cand_kernel(const float* _
     for (int it = 0; it < iters; ++it, dst += dstep, p += npg) {
       const float4 c = cand[p];
       const float thr = cthr[p];
-      float tm[EPT], v[EPT];
-      bool unsafe = nan_flag != 0;
+      float tm[EPT], v[EPT], dm[EPT];
+      // uq_code_fast (quant_device.cuh) on two elements per packed FP32 instruction; the distances to the rounded
+      // values are reduced by a max tree and tested once per (candidate, chunk)
 #pragma unroll
-      for (int j = 0; j < EPT; ++j) tm[j] = uq_code_fast(xv[j], c, two_n, thr, unsafe);
+      for (int j = 0; j < EPT; j += 2) {
+        const float ts0 = fminf(__saturatef(fmaf(xv[j], c.x, c.y)), c.z);
+        const float ts1 = fminf(__saturatef(fmaf(xv[j + 1], c.x, c.y)), c.z);
+        float n0, n1;
+        ffma2(tm[j], tm[j + 1], ts0, ts1, two_n, two_n, c.w, c.w);           // (code - zp) + 1.5*2^23
+        fadd2(n0, n1, c.w, c.w, -tm[j], -tm[j + 1]);                         // -(rounded clamped value)
+        ffma2(dm[j], dm[j + 1], ts0, ts1, two_n, two_n, n0, n1);             // clamped - rint(clamped)
+      }
+#pragma unroll
+      for (int w2 = EPT / 2; w2 > 0; w2 >>= 1) {
+#pragma unroll
+        for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
+      }
+      const bool unsafe = nan_flag != 0 || !(dm[0] <= thr);
       if (unsafe) {                                      // rare: redo the chunk on the IEEE path
         const float2 sz = cand_sz[p];
 #pragma unroll
@@ -666,8 +680,12 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
   for (int ch = lane_chunk; ch < cpr; ch += tpc) {
     const int kc = ch << 3;
     const bool tail = kc + 8 > K;
-    float xs[8], lx[8], e1[8], gm[8];
-    bool clamp_region = false;
+    float xs[8], lx[8], e1[8];
+    // element part of the rounding margin, 6e-7 |lx| + 2e-7: the chunk's LARGEST is used for all of its elements
+    // (conservative: a few more chunks take the IEEE path, still ~1e-4 of them), so the check is ONE threshold per
+    // (candidate, chunk) against the max of |d| instead of an FFMA + FSETP per element; +inf (an element near the
+    // reference's 1e-15 clamp, x <= 0 or NaN) routes the whole chunk to the IEEE path
+    float gmax = 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = (kc + j < K) ? __ldg(xrow + kc + j) : 1.0f;
@@ -675,33 +693,39 @@ __global__ void __launch_bounds__(256) gen_log_cand_lut_kernel(const float* __re
       xs[j] = v;
       lx[j] = -log2f(v);
       e1[j] = SCALED ? lx[j] : __fmul_rn(lx[j], 37.0f);
-      gm[j] = SCALED ? (6e-7f * fabsf(lx[j]) + 2e-7f) : 0.0f;
-      clamp_region |= !(lx[j] <= lim_min);             // near the reference's 1e-15 clamp, x <= 0 or NaN
+      gmax = fmaxf(gmax, !(lx[j] <= lim_min) ? __int_as_float(0x7f800000) : fabsf(lx[j]));
     }
+    gmax = SCALED ? fmaf(6e-7f, gmax, 2e-7f) : (gmax <= 3.0e38f ? 0.0f : gmax);
+    asm volatile("" : "+f"(gmax));       // keep it in a register: the compiler otherwise re-derives it per candidate
     uint16_t* dst = out + (u * ADALOG_P + p_lo + pg) * (int64_t)kpad + kc;
     int p = p_lo + pg;
-    // keep the chunk's clamp flag in a register: the compiler otherwise re-derives it from lx[] per candidate
-    int clamp_flag = clamp_region ? 1 : 0;
-    asm volatile("" : "+r"(clamp_flag));
     for (int it = 0; it < iters; ++it, dst += dstep, p += npg) {
-      const float4 c = cand[p];          // {mul / 2n, off / 2n, lim, q}: 2n is a power of two, the scaling is exact
-      const float half = chalf[p];
+      const float4 c = cand[p];          // {mul / 2n, off / 2n, lim, mul}: 2n is a power of two, the scaling is exact
+      const float lim_d = fmaf(-gmax, c.w, chalf[p]);
       uint32_t row = lut_bias + (uint32_t)((p - p_lo) * lw) * 4u;
       asm volatile("" : "+r"(row));      // one add per element below, not a re-derivation of the row address
-      float v[8];
-      bool unsafe = clamp_flag != 0;
+      float v[8], dm[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; j += 2) {
         // t/2n clamped to [0,1] by the FMA's own saturation (codes >= 2n all read lut[2n] = 0), then
-        // tm = t + 1.5*2^23 in one more FMA: same roundings as fma -> clamp -> add, two ALU-pipe min/max fewer
-        const float ts = __saturatef(fmaf(e1[j], c.x, c.y));
-        const float tm = fmaf(ts, ncode, kMagic);
-        const float d = fmaf(ts, ncode, -__fsub_rn(tm, kMagic));
-        unsafe |= !(fabsf(d) <= fmaf(-gm[j], c.w, half));
-        float val;
-        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(__float_as_uint(tm) * 4u + row));
-        v[j] = val;
+        // tm = t + 1.5*2^23 and d = t - rint(t), two elements per packed FP32 instruction (same IEEE results per lane)
+        const float ts0 = __saturatef(fmaf(e1[j], c.x, c.y));
+        const float ts1 = __saturatef(fmaf(e1[j + 1], c.x, c.y));
+        float tm0, tm1, n0, n1;
+        ffma2(tm0, tm1, ts0, ts1, ncode, ncode, kMagic, kMagic);
+        fadd2(n0, n1, kMagic, kMagic, -tm0, -tm1);
+        ffma2(dm[j], dm[j + 1], ts0, ts1, ncode, ncode, n0, n1);
+        float val0, val1;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(val0) : "r"(__float_as_uint(tm0) * 4u + row));
+        asm("ld.shared.f32 %0, [%1];" : "=f"(val1) : "r"(__float_as_uint(tm1) * 4u + row));
+        v[j] = val0; v[j + 1] = val1;
       }
+#pragma unroll
+      for (int w2 = 4; w2 > 0; w2 >>= 1) {
+#pragma unroll
+        for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
+      }
+      const bool unsafe = !(dm[0] <= lim_d);
       if (unsafe) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = log_value_slow(xs[j], lx[j], SCALED, cscale[p], candq[p], mt, ncode);

@@ -50,7 +50,7 @@ CONFIGS = {1: ('deit_tiny', 4, 32, 'weak'), 2: ('deit_small', 3, 128, 'weak'), 3
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
     summary (profiles/), or None: a bench run cannot measure DRAM traffic itself (never a number taken under a profiler)"""
-    for name in ('r2_ncu_full_lin_fused.json', 'r1_ncu_full_cand_gemm_err_v2.json'):
+    for name in ('r2_ncu_full_lin_fused_i8.json', 'r2_ncu_full_lin_fused_log.json', 'r1_ncu_full_cand_gemm_err_v2.json'):
         path = os.path.join(ROOT, 'profiles', name)
         if os.path.exists(path):
             try:
@@ -558,7 +558,9 @@ def run_ours(args):
                                  other_kernels=[dict(
                                      kernel='fused_cand_gemm_err_kernel (attention sweeps: candidates generated in '
                                             'shared memory + tcgen05 GEMM + error epilogue)',
-                                     bound='TMEM read-out (64 B/clk/SM) and issue slots, see DESIGN.md section 4',
+                                     bound='CUDA-core issue slots: K = 64 per unit, so generating the 128 x K tile and '
+                                           'reducing the 128 x N error cost more instructions than the MMA has clocks '
+                                           '(DESIGN.md section 4; TMEM read-out measured at 320-440 B/clk/SM is not the bound)',
                                      launches=fz_launches, kernel_ms_per_step=fz_ms / max(1, args.steps),
                                      achieved=fz_flops / (fz_ms / 1e3) / 1e12 if fz_ms > 0 else 0.0, unit='TFLOP/s',
                                      share_of_step=fz_ms / max(1e-9, sum(times)))]))
