@@ -16,7 +16,9 @@ KEYS = ['gpu__time_duration.sum', 'sm__cycles_active.avg', 'dram__bytes_read.sum
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__m_xbar2l1tex_read_bytes.sum',
-        'lts__t_sector_hit_rate.pct', 'smsp__inst_executed.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']
+        'lts__t_sector_hit_rate.pct', 'smsp__inst_executed.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum']
 
 
 def raw_page(path):
