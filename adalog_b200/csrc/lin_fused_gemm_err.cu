@@ -233,10 +233,16 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
         const int e = cqi / 37;
         if (e <= 120) val = ldexpf(tl.mt[cqi - e * 37], -e);
       }
-      lut[i] = val;
+      // four candidates interleaved per code: lut[p >> 2][c][p & 3].  The 32 lanes of a producer warp look up four
+      // consecutive candidates x eight elements at once; with one row of 2n + 1 words per candidate they spread over
+      // 4 (2n + 1) words of 32 banks (ncu: 1.5 wavefronts per load); interleaved, two lanes collide only when their codes
+      // differ by a multiple of 8 for the SAME candidate
+      lut[((p >> 2) * lw + c) * 4 + (p & 3)] = val;
     }
     if (w == 0) {
-      for (int i = 0; i < 3; ++i) tl.lut_bias[i] = smem_u32(lut) - 0x2D000000u + (uint32_t)(i * kCandGroups * lw) * 4u;
+      // byte address of lut[(p >> 2)][c][p & 3] = bits(c + (cg >> 2) lw + 1.5*2^23) * 16 + lut_bias[i] + (cg & 3) * 4  (mod 2^32)
+      // for candidate p = cg + kCandGroups i: 16 * bits(1.5*2^23) = 0xB4000000 (mod 2^32)
+      for (int i = 0; i < 3; ++i) tl.lut_bias[i] = smem_u32(lut) - 0xB4000000u + (uint32_t)(i * (kCandGroups / 4) * lw) * 16u;
       float m = __int_as_float(0x7f800000);
       for (int p = 0; p < ADALOG_P; ++p) m = fminf(m, tl.cand[p].z);
       tl.lim_min = m;
@@ -409,11 +415,12 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
     const int w = threadIdx.x - kProdWarp0 * 32;
     const int ch = w & 7, cg = w >> 3;
     const int lw = 2 * a.nl + 1;
-    // AdaLog LUT address = bits(code + row + 1.5*2^23) * 4 + lut_bias (mod 2^32); the row of candidate i is
-    // (cg + 48 i) lw: the cg part rides in the rounding constant kw, the 48 i part in the (uniform) bias -- read back
-    // from shared memory so that ptxas cannot split the constant off again (it rematerialised shift + two adds per
+    // AdaLog LUT address = bits(code + row + 1.5*2^23) * 16 + bias (mod 2^32), see the LUT construction above: the
+    // (cg >> 2) lw part of the row rides in the rounding constant kw, the candidate step and (cg & 3) in the bias -- read
+    // back from shared memory so that ptxas cannot split the constant off again (it rematerialised shift + two adds per
     // element instead of ONE LEA when the value was computed in registers)
-    const uint32_t lb0 = tl.lut_bias[0], lb1 = tl.lut_bias[1], lb2 = tl.lut_bias[kCPT - 1];
+    const uint32_t lb0 = tl.lut_bias[0] + (uint32_t)(cg & 3) * 4u, lb1 = tl.lut_bias[1] + (uint32_t)(cg & 3) * 4u,
+                   lb2 = tl.lut_bias[kCPT - 1] + (uint32_t)(cg & 3) * 4u;
     uint32_t srcs_s = smem_u32(srcs), sA_s = smem_u32(sA);
     asm volatile("" : "+r"(srcs_s), "+r"(sA_s));              // (ptxas otherwise rematerialises the aligned smem base per store)
     float kx[kCPT], ky[kCPT], kw[kCPT], kt[kCPT];
@@ -422,9 +429,9 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
       const int p = min(cg + i * kCandGroups, ADALOG_P - 1);
       const float4 c = tl.cand[p];
       kx[i] = c.x; ky[i] = c.y; kt[i] = tl.cthr[p];
-      // uniform: 1.5*2^23 - zp;  AdaLog: 1.5*2^23 + cg lw for all three, so that the bits of the rounded value index
+      // uniform: 1.5*2^23 - zp;  AdaLog: 1.5*2^23 + (cg >> 2) lw for all of them, so that the bits of the rounded value index
       // the LUT directly (exact ties, where the parity of this constant would matter, always take the IEEE path)
-      kw[i] = GEN == GEN_LOG ? kMagic + (float)(cg * lw) : c.w;
+      kw[i] = GEN == GEN_LOG ? kMagic + (float)((cg >> 2) * lw) : c.w;
     }
     // row p = cg + 48 i of the tile: 128 bytes per row, chunk position swizzled by p & 7 == cg & 7 (48 % 8 == 0)
     const uint32_t so0 = (uint32_t)cg * 128u + (((uint32_t)ch ^ ((uint32_t)cg & 7u)) << 4);
@@ -434,6 +441,20 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
     const float lim_min = GEN == GEN_LOG ? tl.lim_min : 0.0f;
     const int n_gen = n_units * gen_per_unit;                 // (unit, pass) pairs
     uint32_t as = 0, aph = 0;
+    // The source row of the NEXT generation is fetched into registers while the current one is generated: the staging
+    // below then starts from registers instead of waiting ~1.5k clocks for global memory between two barriers, with
+    // the operand ring running empty meanwhile.  (kPre x kProdThreads elements; longer rows load the rest directly.)
+    constexpr int kPre = 6;
+    float pre[kPre];
+    auto fetch_row = [&](int u) {
+      const float* xrow = a.x + (long long)u * a.ldx;
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int k = w + i * kProdThreads;
+        pre[i] = k < a.K ? __ldg(xrow + k) : (GEN == GEN_LOG ? 1.0f : 0.0f);
+      }
+    };
+    if (n_gen > 0) fetch_row(u0);
     for (int gi = 0; gi < n_gen; ++gi) {
       const int u = u0 + (a.streamed ? gi / a.NG : gi);
       {
@@ -447,9 +468,8 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
         // -- so the inner loops test ONE threshold per (candidate, chunk) and +inf routes the chunk to the IEEE path.
         asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads) : "memory");      // everybody is done with the previous unit's values
         const float* xrow = a.x + (long long)u * a.ldx;
-        for (int k = w; k < a.KB * EL; k += kProdThreads) {
-          float v = GEN == GEN_LOG ? 1.0f : 0.0f;
-          if (k < a.K) { v = __ldg(xrow + k); if (GEN == GEN_LOG && a.shift) v = __fadd_rn(v, sh); }
+        auto stage = [&](int k, float v) {
+          if (GEN == GEN_LOG && a.shift && k < a.K) v = __fadd_rn(v, sh);
           const float sv = GEN == GEN_LOG ? -log2f(v) : v;
           // staged per K block as [float4 index q][chunk][4]: the eight 16-byte pieces a quarter warp reads at once are
           // contiguous (one wavefront; the natural layout put them 32 bytes apart: two-way bank conflicts, ncu: 8
@@ -460,8 +480,17 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
 #pragma unroll
           for (int m = 1; m < EPT; m <<= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, m));
           if ((lane & (EPT - 1)) == 0) chunk_g[k / EPT] = GEN == GEN_LOG ? fmaf(6e-7f, g, 2e-7f) * ncode_f : g;
+        };
+        const int kend = a.KB * EL;                             // a multiple of 32: every loop below is warp-uniform
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+          const int k = w + i * kProdThreads;
+          if (k < kend) stage(k, pre[i]);
         }
+        for (int k = w + kPre * kProdThreads; k < kend; k += kProdThreads)
+          stage(k, k < a.K ? __ldg(xrow + k) : (GEN == GEN_LOG ? 1.0f : 0.0f));
         asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads) : "memory");
+        if (gi + 1 < n_gen) fetch_row(u0 + (a.streamed ? (gi + 1) / a.NG : gi + 1));
       }
       for (int kb = 0; kb < a.KB; ++kb) {
         const uint32_t a_tile = sA_s + as * kATile + so0;
@@ -544,8 +573,8 @@ lin_fused_kernel(const __grid_constant__ CUtensorMap tmB, const LArgs a) {
               fadd2(n0, n1, kw[i], kw[i], -tm0, -tm1);
               ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);
               float val0, val1;
-              asm("ld.shared.f32 %0, [%1];" : "=f"(val0) : "r"(__float_as_uint(tm0) * 4u + lb));
-              asm("ld.shared.f32 %0, [%1];" : "=f"(val1) : "r"(__float_as_uint(tm1) * 4u + lb));
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val0) : "r"(__float_as_uint(tm0) * 16u + lb));
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val1) : "r"(__float_as_uint(tm1) * 16u + lb));
               v[j] = val0; v[j + 1] = val1;
             }
 #pragma unroll

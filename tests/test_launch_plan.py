@@ -54,3 +54,55 @@ def test_fused_units_per_cta(groups, ug, K, N):
     assert 1 <= upc <= ug
     cpg = math.ceil(ug / upc)
     assert cpg <= 16                                           # a CTA amortises its fixed-operand load over >= ug/16 units
+
+
+def _lin_args(K, N, U, log, i8, nl):
+    """adalog_lin_fused_args with dummy (non-null, 16-byte aligned) pointers: _grid / _passes only validate and plan"""
+    import ctypes
+    from adalog_b200 import _lib
+    a = _lib.LinFusedArgs()
+    dummy = 1 << 20
+    a.x, a.ldx, a.Bm, a.b_rows = dummy, K, dummy, N
+    a.K, a.N, a.U, a.P, a.n_levels = K, N, U, 128, nl
+    a.gen, a.dtype = (1 if log else 0), (_lib_i8() if i8 else 0)
+    a.cs, a.cz, a.cq, a.shift, a.mtab = dummy, dummy, dummy, None, dummy
+    a.y, a.ldy, a.rs, a.ccs, a.ccb = dummy, N, dummy, dummy, dummy
+    return a, ctypes
+
+
+def _lib_i8():
+    from adalog_b200 import ops
+    return ops.I8
+
+
+@pytest.mark.parametrize('K,N,U,log,i8,nl,passes', [
+    (384, 1152, 25216, False, True, 4, 1),      # DeiT-S qkv int8: all 3 K blocks resident
+    (384, 384, 25216, False, True, 4, 1),
+    (768, 3072, 25216, False, True, 8, 1),      # DeiT-B fc1 int8: 6 K blocks resident
+    (1024, 4096, 6272, False, True, 32, 1),     # Swin-B stage-4 fc1: 8 int8 K blocks + one spare stage still fit: resident
+    (768, 768, 900, False, False, 128, 2),      # 8-bit uniform (bf16 operands), 12 K blocks: streamed, two passes
+    (1536, 384, 25216, True, False, 4, 1),      # DeiT-S fc2 AdaLog: streamed, one 384-column pass
+    (3072, 768, 25216, True, False, 8, 2),      # DeiT-B fc2 AdaLog: two 512-column TMEM passes -> caller keeps the workspace path
+    (100, 52, 777, False, True, 8, 1),          # ragged K and N
+])
+def test_lin_fused_schedule(K, N, U, log, i8, nl, passes):
+    """host-side schedule of the fused linear sweep (no kernel call): grid = one persistent CTA per SM (or per unit),
+    and how often a unit's operand is generated -- the quantity sweep._lin_fused_passes() gates the fused path on"""
+    from adalog_b200 import _lib
+    lib = _lib.load()
+    a, ctypes = _lin_args(K, N, U, log, i8, nl)
+    assert lib.adalog_lin_fused_cand_gemm_err_grid(ctypes.byref(a)) == min(U, sweep.NUM_SMS)
+    assert lib.adalog_lin_fused_cand_gemm_err_passes(ctypes.byref(a)) == passes
+
+
+def test_lin_fused_rejects_bad_arguments():
+    from adalog_b200 import _lib
+    lib = _lib.load()
+    a, ctypes = _lin_args(384, 1150, 100, False, True, 4)              # N not a multiple of 4
+    assert lib.adalog_lin_fused_cand_gemm_err_grid(ctypes.byref(a)) == -2
+    a, ctypes = _lin_args(1536, 384, 100, True, True, 4)               # AdaLog candidates are bf16 operands
+    assert lib.adalog_lin_fused_cand_gemm_err_grid(ctypes.byref(a)) == -2
+    a, ctypes = _lin_args(384, 384, 100, False, True, 4)
+    a.y = None
+    assert lib.adalog_lin_fused_cand_gemm_err_passes(ctypes.byref(a)) == -1
+    assert b'null pointer' in lib.adalog_last_error()
