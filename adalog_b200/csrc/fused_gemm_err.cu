@@ -329,10 +329,24 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
           auto u_gen = [&](int p, float (&tm)[EPT]) -> bool {
             const float4 c = tl.cand[p];
             const float thr = tl.cthr[p];
-            bool unsafe = nan_flag != 0;
+            // uq_code_fast (quant_device.cuh) on two elements per packed FP32 instruction; the distances to the rounded
+            // values are reduced by a max tree and tested once per (candidate, chunk)
+            float dm[EPT];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) tm[j] = uq_code_fast(xv[j], c, ncode_f, thr, unsafe);
-            return unsafe;
+            for (int j = 0; j < EPT; j += 2) {
+              const float ts0 = fminf(__saturatef(fmaf(xv[j], c.x, c.y)), c.z);
+              const float ts1 = fminf(__saturatef(fmaf(xv[j + 1], c.x, c.y)), c.z);
+              float n0, n1;
+              ffma2(tm[j], tm[j + 1], ts0, ts1, ncode_f, ncode_f, c.w, c.w);        // (code - zp) + 1.5*2^23
+              fadd2(n0, n1, c.w, c.w, -tm[j], -tm[j + 1]);                          // -(rounded clamped value)
+              ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);          // clamped - rint(clamped)
+            }
+#pragma unroll
+            for (int w2 = EPT / 2; w2 > 0; w2 >>= 1) {
+#pragma unroll
+              for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
+            }
+            return nan_flag != 0 || !(dm[0] <= thr);
           };
           auto u_fix = [&](int p, float (&tm)[EPT], bool unsafe) {
             if (unsafe) {
@@ -390,18 +404,26 @@ fused_cand_gemm_err_kernel(const __grid_constant__ CUtensorMap tmB, const FArgs 
             const float4 c = tl.cand[p];
             uint32_t row = lut_bias + (uint32_t)(p * lw) * 4u;
             asm volatile("" : "+r"(row));
-            bool unsafe = bad != 0;
+            float dm[EPT];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-              const float ts = __saturatef(__fmul_rn(e1[j], c.x));
-              const float tm = fmaf(ts, ncode_f, kMagic);
-              const float d = fmaf(ts, ncode_f, -__fsub_rn(tm, kMagic));
-              unsafe |= !(fabsf(d) <= kFracSafe);
-              float val;
-              asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(__float_as_uint(tm) * 4u + row));
-              v[j] = val;
+            for (int j = 0; j < EPT; j += 2) {
+              const float ts0 = __saturatef(__fmul_rn(e1[j], c.x));
+              const float ts1 = __saturatef(__fmul_rn(e1[j + 1], c.x));
+              float tm0, tm1, n0, n1;
+              ffma2(tm0, tm1, ts0, ts1, ncode_f, ncode_f, kMagic, kMagic);
+              fadd2(n0, n1, kMagic, kMagic, -tm0, -tm1);
+              ffma2(dm[j], dm[j + 1], ts0, ts1, ncode_f, ncode_f, n0, n1);
+              float val0, val1;
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val0) : "r"(__float_as_uint(tm0) * 4u + row));
+              asm("ld.shared.f32 %0, [%1];" : "=f"(val1) : "r"(__float_as_uint(tm1) * 4u + row));
+              v[j] = val0; v[j + 1] = val1;
             }
-            return unsafe;
+#pragma unroll
+            for (int w2 = EPT / 2; w2 > 0; w2 >>= 1) {
+#pragma unroll
+              for (int j = 0; j < w2; ++j) dm[j] = fmaxf(fabsf(dm[j]), fabsf(dm[j + w2]));
+            }
+            return bad != 0 || !(dm[0] <= kFracSafe);
           };
           auto l_fix = [&](int p, float (&v)[EPT], bool unsafe) {
             if (unsafe) {
