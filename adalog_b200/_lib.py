@@ -87,7 +87,7 @@ SIGNATURES = {
     'adalog_lin_fused_cand_gemm_err_passes': [ctypes.POINTER(LinFusedArgs)],
     'adalog_lin_fused_cand_gemm_err': [ctypes.POINTER(LinFusedArgs), c_vp],
     'adalog_gemm_dequant': [ctypes.POINTER(GemmErrArgs), c_vp, c_i64, c_i64, c_vp],
-    'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp],
+    'adalog_debug_gemm_tile': [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
 }
 
 # exported functions that do not return an int status (bound separately in load())

@@ -499,22 +499,11 @@ int adalog_gemm_dequant(const adalog_gemm_err_args* a, float* out, int64_t ldo, 
   return launch(a, nullptr, (cudaStream_t)stream, out, ldo, m_rows);
 }
 
-int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, int dtype, void* stream) {
-  ADALOG_REQUIRE(A && Bm && D && KB > 0 && N > 0, -1, "debug_gemm_tile: bad arguments");
-  // y = 0, rs = 1: scratch taken from D's tail is not available, so use small static device buffers
-  static float* zeros = nullptr;
-  static float* ones = nullptr;
-  static double* part = nullptr;
-  if (!zeros) {
-    float h1[kBM];
-    for (int i = 0; i < kBM; ++i) h1[i] = 1.0f;
-    if (cudaMalloc(&zeros, 65536 * sizeof(float)) != cudaSuccess || cudaMalloc(&ones, kBM * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&part, 64 * kBM * sizeof(double)) != cudaSuccess)
-      return fail(-30, "debug_gemm_tile: cudaMalloc failed");
-    cudaMemset(zeros, 0, 65536 * sizeof(float));
-    cudaMemcpy(ones, h1, sizeof(h1), cudaMemcpyHostToDevice);
-  }
-  ADALOG_REQUIRE(N <= 65536, -1, "debug_gemm_tile: N too large");
+int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, const float* zeros, const float* ones,
+                           double* partial, int dtype, void* stream) {
+  // y = 0, rs = 1 come from the caller (zeros [N], ones [128], partial [64 * 128] doubles): no library-owned device state
+  ADALOG_REQUIRE(A && Bm && D && zeros && ones && partial && KB > 0 && N > 0, -1, "debug_gemm_tile: bad arguments");
+  double* part = partial;
   adalog_gemm_err_args a;
   memset(&a, 0, sizeof(a));
   a.A = A; a.Bm = Bm; a.a_rows = kBM; a.b_rows = N; a.KB = KB; a.N = N; a.dtype = dtype;

@@ -495,8 +495,11 @@ def debug_gemm_tile(A, Bm):
     ka = A.shape[1]
     N = Bm.shape[0]
     D = torch.zeros(128, N, dtype=torch.float32, device=A.device)
+    zeros = torch.zeros(max(N, 1), dtype=torch.float32, device=A.device)
+    ones = torch.ones(P_TILE, dtype=torch.float32, device=A.device)
+    partial = torch.empty(64 * P_TILE, dtype=torch.float64, device=A.device)
     call('adalog_debug_gemm_tile', _p(A.contiguous()), _p(Bm.contiguous()), ka // (2 * BK if i8 else BK), N, _p(D),
-         I8 if i8 else BF16, _stream())
+         _p(zeros), _p(ones), _p(partial), I8 if i8 else BF16, _stream())
     return D
 
 

@@ -248,8 +248,10 @@ int adalog_lin_fused_cand_gemm_err(const adalog_lin_fused_args* a, void* stream)
 int adalog_gemm_dequant(const adalog_gemm_err_args* a, float* out, int64_t ldo, int64_t m_rows, void* stream);
 
 /* plain (non-candidate) debug GEMM through the same tcgen05 pipeline: D[m,n] FP32 for A [128,ka], Bm [N,ka];
- * used by the tests to validate descriptors / swizzle / TMEM addressing in isolation. */
-int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, int dtype, void* stream);
+ * used by the tests to validate descriptors / swizzle / TMEM addressing in isolation.  Scratch comes from the caller
+ * (zeros [N] floats holding 0, ones [128] floats holding 1, partial [64 * 128] doubles): the library owns no device state. */
+int adalog_debug_gemm_tile(const void* A, const void* Bm, int KB, int N, float* D, const float* zeros, const float* ones,
+                           double* partial, int dtype, void* stream);
 
 #ifdef __cplusplus
 }
