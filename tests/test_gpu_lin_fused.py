@@ -126,3 +126,39 @@ def test_log_sweep_matches_two_kernel_path(tokens, in_f, out_f, bits):
     perm = torch.randperm(128, device=DEV)
     again, _ = _both(lambda: sweep.linear_err_log(ctx, W3, b, wq, lq, sc[:, perm].contiguous(), qc[:, perm].contiguous()))
     assert torch.equal(again, fused[:, perm])
+
+
+def test_fixed_operand_cache_follows_quantizer_updates():
+    """The fixed (weight / activation) operand of a sweep is cached on the calibration context and keyed on the fixed
+    side's quantizer parameters: scoring, updating a parameter through quantizers/_ste.assign and scoring again must
+    give exactly what a cache-free evaluation gives (a stale operand would be off by far more than rounding)."""
+    from adalog_b200 import sweep
+    from adalog_b200.quantizers._ste import assign
+    bits, nl = 4, 8
+    x, W, b, y = _setup(1576, 192, 384)
+    W3 = W.view(1, 384, 192)
+    wcs, wcz = O.weight_candidates(W, 1, nl, 128)
+    acs, acz = O.activation_candidates(x, nl, 128, False)
+    wq = _uq(bits, torch.nn.Parameter(wcs[64].clone()), torch.nn.Parameter(wcz[64].clone().float()))
+    aq = _uq(bits, torch.nn.Parameter(acs[:, 64].clone()), torch.nn.Parameter(acz[:, 64].clone().float()))
+    ctx = sweep.LinearCtx(x, y, 384)
+
+    def fresh(fn):
+        old = sweep.FIXED_CACHE
+        sweep.FIXED_CACHE = False
+        try:
+            return fn()
+        finally:
+            sweep.FIXED_CACHE = old
+
+    score_a = lambda: sweep.linear_err_a(ctx, W3, b, wq, acs, acz, nl)
+    score_w = lambda: sweep.linear_err_w(ctx, W3, b, aq, wcs, wcz, nl)
+    for score, param, new in ((score_a, wq.scale, wcs[90]), (score_a, wq.zero_point, wcz[30].float()),
+                              (score_w, aq.scale, acs[:, 20]), (score_w, aq.zero_point, acz[:, 100].float())):
+        first = score()
+        assert torch.equal(first, score()), 'a cache hit must reproduce the evaluation bit for bit'
+        assert torch.equal(first, fresh(score))
+        assign(param, new.clone().reshape(param.shape))
+        second = score()
+        assert torch.equal(second, fresh(score)), 'stale fixed operand after a quantizer update'
+        assert not torch.equal(first, second)
