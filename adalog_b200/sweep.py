@@ -19,7 +19,9 @@ from . import _const, ops
 from .quantizers._ste import flag as _flag
 from .utils import dist as adist
 
-WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '2048')) << 20
+# operand workspace of the generator -> GEMM path (two buffers of half this size).  8 GiB of the 180 GB: fewer, larger
+# chunks -- the DeiT-B fc2 AdaLog sweep (9.9 GB of candidate operand) measured 16.1 ms with 2 GiB, 14.7 ms with 8 GiB
+WS_BYTES = int(os.environ.get('ADALOG_B200_WS_MB', '8192')) << 20
 NUM_SMS = 148
 R_BASE = 37.0
 # uniform x uniform sweeps (every quantizer up to 7 bits: |code - zp| <= 127) run on the INT8 tensor cores
