@@ -28,6 +28,16 @@ def linspace01(n, device):
 
 
 @functools.lru_cache(maxsize=None)
+def _linspace01_centered(n, dtype_key):
+    return _linspace01(n, dtype_key) - 0.5       # on the device, as the reference does (linear.py:497-502)
+
+
+def linspace01_centered(n, device):
+    """linspace01(n) - 0.5 (the refinement offsets of FPCS before scaling by the grid pitch), cached per device"""
+    return _linspace01_centered(int(n), _key(device))
+
+
+@functools.lru_cache(maxsize=None)
 def _int_range(lo, hi, dk):
     return torch.tensor(range(lo, hi)).to(torch.device(*dk) if dk[1] is not None else dk[0])
 

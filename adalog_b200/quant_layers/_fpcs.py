@@ -31,19 +31,21 @@ def refine(scales, aux, delta, score, axis, new_cnt, width, steps, floor=None):
     best_a = torch.gather(aux, dim=axis, index=idx)
     left = steps - 1
     while left > 0:
-        ramp = _const.linspace01(new_cnt, dev)
+        # linspace(0, 1, new_cnt) - 0.5 as the reference computes it (FP32, same op), cached per (count, device);
+        # repeat_interleave(n) as expand + reshape: same values, one copy kernel instead of five launches
+        ramp_c = _const.linspace01_centered(new_cnt, dev)
         if axis == 0:
-            offs = (ramp.view(-1, *([1] * (scales.dim() - 1))) - 0.5) * delta
+            offs = ramp_c.view(-1, *([1] * (scales.dim() - 1))) * delta
             delta = delta / (new_cnt - 0.5)
             scales = (best_s.unsqueeze(1) + offs.unsqueeze(0)).reshape(-1, *scales.shape[1:])
-            aux = best_a.repeat_interleave(new_cnt, dim=0)
+            aux = best_a.unsqueeze(1).expand(-1, new_cnt, *best_a.shape[1:]).reshape(-1, *best_a.shape[1:])
         else:
-            offs = (ramp[None, :] - 0.5) * delta
+            offs = ramp_c[None, :] * delta
             delta = delta / (new_cnt - 0.5)
             scales = (best_s.unsqueeze(-1) + offs.unsqueeze(-2)).reshape(*scales.shape[:-1], -1)
             if floor is not None:
                 scales = scales.clamp(min=floor)
-            aux = best_a.repeat_interleave(new_cnt, dim=-1)
+            aux = best_a.unsqueeze(-1).expand(*best_a.shape, new_cnt).reshape(*best_a.shape[:-1], -1)
         idx = score(scales, aux, 1 if left == 1 else width)
         if left > 1:
             best_s = torch.gather(scales, dim=axis, index=idx)

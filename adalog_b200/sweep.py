@@ -250,7 +250,8 @@ def linear_err_w_self(weight3, cs, cz, n_levels):
     n_V, rows, in_f = weight3.shape
     c2, z2 = _cand2d(cs, cz)
     esum = ops.sweep_err_w_self(_f32(weight3).reshape(-1, in_f), c2, z2, n_levels)
-    return (-(esum / in_f)).float().reshape(cs.shape[0], n_V, rows)
+    # similarity = -(sum / count); written as sum / -(count): bit-identical in IEEE arithmetic, one kernel less
+    return (esum / -(in_f)).float().reshape(cs.shape[0], n_V, rows)
 
 
 def linear_err_a_self(ctx, cs, cz, n_levels, channel_wise):
@@ -258,7 +259,7 @@ def linear_err_a_self(ctx, cs, cz, n_levels, channel_wise):
     esum = ops.sweep_err_a_self(ctx.x2d, _f32(cs), _f32(cz), n_levels, channel_wise)
     esum = adist.all_reduce_sum(esum)
     denom = ctx.tok_per_sample * (1 if channel_wise else ctx.x2d.shape[1])
-    return (-(esum / denom)).float()
+    return (esum / -(denom)).float()
 
 
 def _i8_ok(*n_levels):
@@ -453,7 +454,7 @@ def linear_err_a(ctx, weight3, bias, wq, cs, cz, n_levels_a, y2d=None):
         res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, y, out_f, rs, None, 1 << 62, 1, s_w, cb,
                             k_true=in_f, i8=i8)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
-    return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
+    return (res[:, :P] / -((ctx.tok_per_sample * out_f))).float()
 
 
 def linear_err_a_twin(ctx, weight3, bias, wq, s_neg, cands, n_levels):
@@ -505,7 +506,7 @@ def linear_err_log(ctx, weight3, bias, wq, aq, cs, cq):
         res = run_cand_gemm(gen, ntok, ka, ntok, Bm, 0, out_f, ctx.y2d, out_f, rs, None, 1 << 62, 1, s_w, cb,
                             k_true=in_f)
     res = adist.all_reduce_sum(res.sum(dim=0, keepdim=True))
-    return (-(res[:, :P] / (ctx.tok_per_sample * out_f))).float()
+    return (res[:, :P] / -((ctx.tok_per_sample * out_f))).float()
 
 
 # ================================================================================================
@@ -543,9 +544,9 @@ def _matmul_reduce(res, ctx, P, head_channel_wise, pool_heads, n_cols_total):
     res = res.view(ctx.Bn, ctx.H, ops.P_TILE).sum(dim=0)          # [H, 128]
     res = adist.all_reduce_sum(res)
     if head_channel_wise and not pool_heads:
-        return (-(res[:, :P] / n_cols_total)).t().float().contiguous()      # [P, H]
+        return (res[:, :P] / -(n_cols_total)).t().float().contiguous()      # [P, H]
     tot = res.sum(dim=0)
-    return (-(tot[:P] / (n_cols_total * ctx.H))).float()                    # [P]
+    return (tot[:P] / -((n_cols_total * ctx.H))).float()                    # [P]
 
 
 FUSED = os.environ.get('ADALOG_B200_FUSED', '1') == '1'
@@ -728,4 +729,4 @@ def conv_err_w(ctx, weight2d, bias, cs, cz, n_levels_w):
     ntok = ctx.yT.shape[1]
     res = run_cand_gemm(gen, oc, ka, 1, ctx.x3, 0, ntok, ctx.yT, ntok, rs, rb, 1, oc, k_true=K)
     res = adist.all_reduce_sum(res)
-    return (-(res[:, :P] / ctx.pos_per_sample)).t().float().contiguous()
+    return (res[:, :P] / -(ctx.pos_per_sample)).t().float().contiguous()
