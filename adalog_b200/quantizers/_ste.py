@@ -29,6 +29,9 @@ def invalidate_caches(module):
     for m in module.modules():
         m.__dict__.pop('_tc_cache', None)
         m.__dict__.pop('_pct_cache', None)
+        ctx = m.__dict__.get('_ctx')               # fixed operands of a search in progress (sweep._cached_fixed)
+        if ctx is not None:
+            ctx.__dict__.pop('_fixed_cache', None)
         for t in list(m.parameters(recurse=False)) + list(m.buffers(recurse=False)):
             for attr in ('_adalog_zr', '_adalog_flag'):
                 if hasattr(t, attr):

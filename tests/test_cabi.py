@@ -43,3 +43,12 @@ def test_integration_stub_struct_matches_binding():
     block = text[text.index('class _GemmErrArgs'):text.index('def _check')]
     names = re.findall(r"\('(\w+)',\s*ctypes\.", block)
     assert names == [f[0] for f in _lib.GemmErrArgs._fields_]
+
+
+def test_integration_lin_fused_stub_matches_binding():
+    """same for the adalog_lin_fused_args stub"""
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = text[text.index('class _LinFusedArgs'):text.index('a = _LinFusedArgs(')]
+    names = re.findall(r"\('(\w+)',\s*ctypes\.", block)
+    assert names == [f[0] for f in _lib.LinFusedArgs._fields_]
+

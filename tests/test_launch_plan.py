@@ -106,3 +106,37 @@ def test_lin_fused_rejects_bad_arguments():
     a.y = None
     assert lib.adalog_lin_fused_cand_gemm_err_passes(ctypes.byref(a)) == -1
     assert b'null pointer' in lib.adalog_last_error()
+
+
+def test_fixed_operand_cache_keys(monkeypatch):
+    """host logic of sweep._cached_fixed (no kernel): one entry per role on the calibration context, rebuilt exactly when
+    a key tensor is written through quantizers/_ste.assign (version bump) or replaced, dropped by invalidate_caches"""
+    import torch
+    from adalog_b200.quantizers._ste import assign, invalidate_caches
+
+    class Ctx:
+        pass
+
+    ctx, calls = Ctx(), []
+    scale, zp = torch.nn.Parameter(torch.ones(4)), torch.nn.Parameter(torch.zeros(4))
+
+    def get():
+        return sweep._cached_fixed(ctx, 'weight', (8, True) + sweep._pkey(scale, zp),
+                                   lambda: calls.append(1) or float(scale.sum()))
+    assert get() == 4.0 and get() == 4.0 and len(calls) == 1                 # hit
+    assign(scale, torch.full((4,), 2.0))
+    assert get() == 8.0 and len(calls) == 2                                  # version bump -> rebuilt
+    assert get() == 8.0 and len(calls) == 2
+    with torch.no_grad():
+        scale.data.fill_(3.0)                                                # a write through .data is NOT seen ...
+    assert get() == 8.0 and len(calls) == 2
+
+    class Mod(torch.nn.Module):
+        pass
+    m = Mod()
+    m.__dict__['_ctx'] = ctx
+    invalidate_caches(m)                                                     # ... until the caller invalidates
+    assert get() == 12.0 and len(calls) == 3
+    assert sweep._cached_fixed(None, 'weight', (), lambda: 7) == 7            # no context: no caching
+    monkeypatch.setattr(sweep, 'FIXED_CACHE', False)
+    assert get() == 12.0 and len(calls) == 4                                 # switched off: always rebuilt
